@@ -1,0 +1,148 @@
+"""Independent cross-checks of the oracle's third-party restatements (acados ERK sensitivities and
+the HPIPM QP solve), built the way the survey probe was: torch autograd for the
+Jacobians of the RK4 map, dense condensing + scipy BVLS (an exact active-set method) for the box-QP.
+CPU only."""
+import numpy as np
+import pytest
+import torch
+from scipy.optimize import lsq_linear
+
+from oracle import oracle as orc
+
+torch.set_default_dtype(torch.float64)
+
+
+def f_torch(quad, x, u, gp=None, alpha=None):
+    mass, T = quad[0], quad[1]
+    J, xf, yf, zt, g = quad[2:5], quad[5:9], quad[9:13], quad[13:17], quad[17:20]
+    q, v, r = x[3:7], x[7:10], x[10:13]
+    w, a, b, c = q
+    R = torch.stack([
+        torch.stack([1 - 2 * (b * b + c * c), 2 * (a * b - w * c), 2 * (a * c + w * b)]),
+        torch.stack([2 * (a * b + w * c), 1 - 2 * (a * a + c * c), 2 * (b * c - w * a)]),
+        torch.stack([2 * (a * c - w * b), 2 * (b * c + w * a), 1 - 2 * (a * a + b * b)])])
+    Om = torch.stack([
+        torch.stack([0 * r[0], -r[0], -r[1], -r[2]]), torch.stack([r[0], 0 * r[0], r[2], -r[1]]),
+        torch.stack([r[1], -r[2], 0 * r[0], r[0]]), torch.stack([r[2], r[1], -r[0], 0 * r[0]])])
+    fq = 0.5 * Om @ q
+    ft = u * T
+    ab = torch.stack([0 * ft[0], 0 * ft[0], ft.sum() / mass])
+    if gp is not None:
+        vb = R.T @ v
+        mus = []
+        for d in range(3):
+            L, sf = gp.theta[d, 0], gp.theta[d, 1]
+            k = sf ** 2 * torch.exp(-0.5 * (vb[d] - torch.tensor(gp.X[d])) ** 2 / L ** 2)
+            mus.append(k @ torch.tensor(alpha[d]))
+        ab = ab + torch.stack(mus)
+    fv = R @ ab - torch.tensor(g)
+    fr = torch.stack([
+        (ft @ torch.tensor(yf) + (J[1] - J[2]) * r[1] * r[2]) / J[0],
+        (-(ft @ torch.tensor(xf)) + (J[2] - J[0]) * r[2] * r[0]) / J[1],
+        (ft @ torch.tensor(zt) + (J[0] - J[1]) * r[0] * r[1]) / J[2]])
+    return torch.cat([v, fq, fv, fr])
+
+
+def rk4_torch(quad, x, u, dt, gp=None, alpha=None):
+    k1 = f_torch(quad, x, u, gp, alpha)
+    k2 = f_torch(quad, x + dt / 2 * k1, u, gp, alpha)
+    k3 = f_torch(quad, x + dt / 2 * k2, u, gp, alpha)
+    k4 = f_torch(quad, x + dt * k3, u, gp, alpha)
+    return x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+
+
+def _gp(M=20, vmax=10.0, theta=(3.0, 0.1, 0.01), seed=0):
+    rng = np.random.default_rng(seed)
+    gp = orc.GPSpec(np.tile(np.linspace(-vmax, vmax, M), (3, 1)), np.array(theta))
+    mu = 0.5 * rng.standard_normal((3, M))
+    return gp, gp.alpha(mu)
+
+
+@pytest.mark.parametrize("use_gp", [False, True])
+def test_linearization_vs_autograd(use_gp):
+    rng = np.random.default_rng(1)
+    quad = orc.quad_hummingbird()
+    gp, alpha = _gp() if use_gp else (None, None)
+    for _ in range(5):
+        x = np.concatenate([rng.uniform(-2, 2, 3), [1, 0, 0, 0] + 0.3 * rng.standard_normal(4),
+                            rng.uniform(-6, 6, 3), rng.uniform(-2, 2, 3)])
+        u = rng.uniform(0, 1, 4)
+        dt = 0.05
+        Phi, A, B = orc.linearize(quad, x, u, dt, gp, alpha)
+        xt, ut = torch.tensor(x), torch.tensor(u)
+        Pt = rk4_torch(quad, xt, ut, dt, gp, alpha)
+        At, Bt = torch.autograd.functional.jacobian(lambda a, b: rk4_torch(quad, a, b, dt, gp, alpha), (xt, ut))
+        assert np.abs(Phi - Pt.numpy()).max() < 1e-13
+        assert np.abs(A - At.numpy()).max() < 1e-12
+        assert np.abs(B - Bt.numpy()).max() < 1e-12
+        # structural facts the CUDA kernels rely on: d Phi / d p = [I;0]
+        assert np.array_equal(A[:, :3], np.eye(13)[:, :3])
+
+
+def _condensed_bvls(A, B, c, x0, Qd, QNd, Rd, q, r, lb, ub):
+    N = A.shape[0]
+    G = np.zeros((N + 1, 13, 4 * N)); g0 = np.zeros((N + 1, 13)); g0[0] = x0
+    for k in range(N):
+        G[k + 1] = A[k] @ G[k]
+        G[k + 1][:, 4 * k:4 * k + 4] += B[k]
+        g0[k + 1] = A[k] @ g0[k] + c[k]
+    H = np.zeros((4 * N, 4 * N)); gr = np.zeros(4 * N)
+    for k in range(N + 1):
+        Qk = QNd if k == N else Qd
+        H += G[k].T @ (Qk[:, None] * G[k]); gr += G[k].T @ (Qk * g0[k] + q[k])
+    H += np.diag(np.tile(Rd, N)); gr += r.ravel()
+    L = np.linalg.cholesky(H)
+    res = lsq_linear(L.T, -np.linalg.solve(L, gr), bounds=(lb, ub), method="bvls", tol=1e-15, max_iter=2000)
+    u = res.x
+    x = g0 + G @ u
+    return x, u.reshape(N, 4)
+
+
+@pytest.mark.parametrize("case", ["interior", "saturated", "gp"])
+def test_rti_step_vs_condensed_bvls(case):
+    rng = np.random.default_rng(7)
+    quad = orc.quad_hummingbird()
+    N, dt = 20, 0.05
+    gp, alpha = _gp() if case == "gp" else (None, None)
+    # a plausible non-trivial iterate: hover-ish rollout
+    xit = np.zeros((N + 1, 13)); uit = np.full((N, 4), 0.3) + 0.05 * rng.standard_normal((N, 4))
+    xit[0] = np.concatenate([[0, 0, 3], [1, 0, 0, 0], [1.0, -0.5, 0.2], [0, 0, 0]])
+    for k in range(N):
+        xit[k + 1] = orc.rk4(quad, xit[k], uit[k], dt, gp, alpha)
+    x0 = xit[0] + 0.05 * rng.standard_normal(13)
+    amp = 25.0 if case == "saturated" else 2.0
+    xref = np.zeros((N, 13)); xref[:, 3] = 1
+    xref[:, 0] = amp * np.linspace(0.1, 1, N); xref[:, 2] = 3 + 0.3 * amp * np.linspace(0, 1, N)
+    yref, yref_e = orc.make_yref(xref)
+    xo, uo = xit.copy(), uit.copy()
+    r = orc.rti_step(quad, dt, N, x0, yref, yref_e, xo, uo, gp=gp, alpha=alpha, return_lin=True)
+    assert r["status"] == 0
+    A, B, Phi = r["A"], r["B"], r["Phi"]
+    c = np.stack([Phi[k] - A[k] @ xit[k] - B[k] @ uit[k] for k in range(N)])
+    Qd, QNd, Rd = dt * orc.W_DIAG[:13], orc.WE_DIAG, dt * orc.W_DIAG[13:]
+    q = np.concatenate([-Qd * yref[:, :13], (-QNd * yref_e)[None]])
+    rr = -Rd * yref[:, 13:]
+    xb, ub = _condensed_bvls(A, B, c, x0, Qd, QNd, Rd, q, rr, 0.0, 1.0)
+    nact = int(((ub < 1e-9) | (ub > 1 - 1e-9)).sum())
+    if case == "saturated":
+        assert nact > 8
+    assert np.abs(uo - ub).max() < 2e-9, (np.abs(uo - ub).max(), nact)
+    assert np.abs(xo - xb).max() < 2e-8 * max(1.0, np.abs(xb).max())
+
+
+def test_ipm_without_polish_is_tight():
+    """The IPM alone (mu -> 1e-13) must already sit within 1e-8 of the polished (exact) answer."""
+    rng = np.random.default_rng(3)
+    quad = orc.quad_hummingbird()
+    N, dt = 20, 0.05
+    xit = np.zeros((N + 1, 13)); uit = np.zeros((N, 4))
+    x0 = np.concatenate([[0.5, -0.2, 3], [1, 0, 0, 0], [0, 0, 0], [0, 0, 0]])
+    xref = np.zeros((N, 13)); xref[:, 3] = 1; xref[:, 0] = np.linspace(0, 20, N); xref[:, 2] = 3
+    yref, yref_e = orc.make_yref(xref)
+    for step in range(3):
+        xa, ua, xb, ub = xit.copy(), uit.copy(), xit.copy(), uit.copy()
+        ra = orc.rti_step(quad, dt, N, x0, yref, yref_e, xa, ua, polish=True)
+        rb = orc.rti_step(quad, dt, N, x0, yref, yref_e, xb, ub, polish=False)
+        assert ra["status"] == 0 and rb["status"] == 1
+        assert np.abs(ua - ub).max() < 1e-8
+        xit, uit = xa, ua
