@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — closed-loop RTI-MPC + RGP control steps/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one closed-loop control step of EVERY vehicle on this rank: reference chunk -> RTI solve (RK4+sens,
+Riccati IPM) -> u0 -> nominal prediction -> drag residual -> RGP regress x3 -> alpha, plus the plant period that
+closes the loop; everything resident on the GPU.  Workload = BASELINE configs[1]: 4096 independent quads per GPU,
+N=20, per-vehicle RGP (3 axes x 20 basis points), random-smooth references.  Vehicles shard over
+ranks with no data-path collective (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "closed_loop_rti_mpc_rgp_control_steps_per_sec"
+UNIT = "control_steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="vehicles per GPU")
+    ap.add_argument("--nodes", type=int, default=20)
+    ap.add_argument("--basis", type=int, default=20)
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--workload", default="random_smooth", choices=["random_smooth", "lemniscate"])
+    ap.add_argument("--cpu-sample-vehicles", type=int, default=0, help="0 = auto (about 15 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": f"{a.batch} independent quads per GPU, N={a.nodes}, per-vehicle RGP 3x{a.basis} basis points, "
+                        f"{a.workload} references, hummingbird model, closed loop with plant (BASELINE configs[1])",
+            "vehicles_per_gpu": a.batch, "n_nodes": a.nodes, "n_basis": a.basis, "t_horizon": 1.0,
+            "references": a.workload, "sharding": f"vehicles x{n_gpus} ranks, no collective",
+            "l2": "per-step working set (stage tiles 136 MB + factors 47 MB + RGP covariances 39 MB at the default "
+                  "shape) exceeds the 126 MB L2; no explicit flush"}
+
+
+def make_trajectories(a, first_vehicle, count, K):
+    from mpc_quad_ros_b200.trajectory import lemniscate_trajectories, random_smooth_trajectories
+    dt = 1.0 / a.nodes
+    # per-vehicle Philox stream (seed 1234 + global vehicle index): a rank generates only its own vehicles
+    gen = lemniscate_trajectories if a.workload == "lemniscate" else random_smooth_trajectories
+    return gen(count, K, dt, seed=1234 + first_vehicle)
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+
+def cpu_closed_loop(a, traj, x0, steps, nthreads):
+    """the oracle's closed loop (oracle/qmpc_oracle.c, OpenMP over vehicles) on a bounded sample; returns steps/s"""
+    from oracle import oracle as orc
+    dt = 1.0 / a.nodes
+    gp = orc.GPSpec(np.tile(np.linspace(-10, 10, a.basis), (3, 1)), np.array([3.0, 0.1, 0.01])) if a.basis else None
+    loop = orc.ClosedLoop(orc.quad_hummingbird(), dt, a.nodes, traj, x0, gp=gp, nthreads=nthreads)
+    t0 = time.perf_counter()
+    r = loop.run(steps, log=True)
+    el = time.perf_counter() - t0
+    return traj.shape[0] * steps / el, el, float(r["iters"].mean())
+
+
+def reference_arm(a):
+    """--impl reference: the reference's CPU path (C oracle port of acados RTI + numpy RGP, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    nthreads = orc.max_threads()
+    # bounded sample of the same workload: first vehicles of the same trajectories, `steps` control steps
+    Bs = a.cpu_sample_vehicles or max(nthreads, 4 * nthreads)
+    K = a.warmup + a.steps + a.nodes + 2
+    traj = make_trajectories(a, 0, Bs, K)
+    x0 = traj[:, 0, :].copy()
+    dt = 1.0 / a.nodes
+    gp = orc.GPSpec(np.tile(np.linspace(-10, 10, a.basis), (3, 1)), np.array([3.0, 0.1, 0.01])) if a.basis else None
+    loop = orc.ClosedLoop(orc.quad_hummingbird(), dt, a.nodes, traj, x0, gp=gp, nthreads=nthreads)
+    loop.run(a.warmup, log=False)
+    t0 = time.perf_counter()
+    loop.run(a.steps, log=False)
+    el = time.perf_counter() - t0
+    val = Bs * a.steps / el
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * el / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port",
+                             "sample": f"{Bs} vehicles x {a.steps} steps of the same workload (C oracle, OpenMP)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [t.strip() for t in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+
+def flops_per_step(N, M, n_ipm):
+    """ALGORITHMIC flops per vehicle-step: N*(22116+108M) + n_ipm*12067*N + 24M^2+45M + 2000"""
+    return N * (22116 + 108 * M) + n_ipm * 12067 * N + 24 * M * M + 45 * M + 2000
+
+
+def b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        graft.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist.barrier()
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    from mpc_quad_ros_b200 import _capi
+    from mpc_quad_ros_b200.execute_trajectory import ClosedLoop
+    from mpc_quad_ros_b200.gp.GPE import GPEnsemble
+    from mpc_quad_ros_b200.quad import Quadrotor3D
+    from mpc_quad_ros_b200.quad_opt import quad_optimizer
+    lib = _capi.lib()
+
+    B, N, M = a.batch, a.nodes, a.basis
+    K = a.warmup + a.steps + N + 2
+    traj_np = make_trajectories(a, rank * B, B, K)
+    x0_np = traj_np[:, 0, :].copy()
+
+    def make_loop():
+        quad = Quadrotor3D(drag=True, batch=B, device=dev).set_hummingbird_params()
+        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B, device=dev) if M else None
+        opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision)
+        return ClosedLoop(quad, opt, torch.as_tensor(traj_np), torch.as_tensor(x0_np))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- value: everything resident, K timed steps
+    loop = make_loop()
+    for _ in range(a.warmup):
+        loop.step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.qmpc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loop.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.qmpc_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    st, it = loop.opt.solver_status()
+    n_ipm_last = float(it.double().mean().item())
+    bad = int((st != 0).sum().item())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * a.steps / (ms_max * 1e-3)
+
+    # ---------------- roofline leg: same steps again with cudaEvents around the two solve kernels + per-step latency
+    loop2 = make_loop()
+    for _ in range(a.warmup):
+        loop2.step()
+    torch.cuda.synchronize()
+    _capi.check(lib.qmpc_timing_enable(loop2.opt._h, 1))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    iters_sum = 0.0
+    evs[0].record()
+    for s in range(a.steps):
+        loop2.step()
+        evs[s + 1].record()
+    torch.cuda.synchronize()
+    ms_lin, ms_ipm, cnt = C.c_double(), C.c_double(), C.c_int()
+    _capi.check(lib.qmpc_timing_read(loop2.opt._h, C.byref(ms_lin), C.byref(ms_ipm), C.byref(cnt)))
+    _capi.check(lib.qmpc_timing_enable(loop2.opt._h, 0))
+    lat = np.array([evs[s].elapsed_time(evs[s + 1]) for s in range(a.steps)])
+    # mean IPM iterations over a few sampled steps of a third short pass (host reads are outside any timed region)
+    loop3 = make_loop()
+    n_ipm = []
+    for s in range(a.warmup + min(a.steps, 20)):
+        loop3.step()
+        if s >= a.warmup:
+            n_ipm.append(float(loop3.opt.solver_status()[1].double().mean().item()))
+    n_ipm_mean = float(np.mean(n_ipm)) if n_ipm else n_ipm_last
+    peak = C.c_double()
+    _capi.check(lib.qmpc_fma_peak(a.precision, C.byref(peak), _capi.stream_ptr()))
+    ipm_ms = ms_ipm.value / max(cnt.value, 1)
+    ipm_flops = B * n_ipm_mean * 12067 * N            # algorithmic flops of the IPM kernel per launch (SURVEY §8d F_ipm)
+    achieved = ipm_flops / (ipm_ms * 1e-3) / 1e12 if ipm_ms > 0 else 0.0
+    roofline = {"kernel": "qmpc_ipm_kernel", "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
+                "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                "peak_source": "measured in this run by qmpc_fma_peak (register-resident FMA microbenchmark); "
+                               "MEASURED_PEAKS.json has no FMA figure",
+                "ms_per_launch": ipm_ms, "ms_linearize_per_launch": ms_lin.value / max(cnt.value, 1),
+                "share_of_step": ipm_ms / (ms / a.steps) if ms > 0 else None,
+                "n_ipm_mean": n_ipm_mean, "algorithmic_flops_per_vehicle_step": flops_per_step(N, M, n_ipm_mean),
+                "whole_step_tflops": value / world * flops_per_step(N, M, n_ipm_mean) / 1e12}
+
+    # ---------------- e2e: host buffers in, host buffers out, through the Python API (pinned memory)
+    e2e = None
+    if not a.no_e2e:
+        rec = make_loop()
+        xs, us = rec.run(a.warmup + a.steps, record=True)          # states a closed loop really visits
+        torch.cuda.synchronize()
+        xs_host = xs.cpu().pin_memory()
+        traj_host = torch.as_tensor(traj_np).pin_memory()
+        lp = make_loop()
+        x_dev = torch.empty((B, 13), dtype=torch.float64, device=dev)
+        ref_dev = torch.empty((B, N, 13), dtype=torch.float64, device=dev)
+        u_host = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+        xpp = torch.zeros((B, 13), dtype=torch.float64, device=dev)
+        u_dev = torch.empty((B, 4), dtype=torch.float64, device=dev)
+
+        def e2e_step(i):
+            x_dev.copy_(xs_host[i], non_blocking=True)
+            ref_dev.copy_(traj_host[:, i:i + N, :], non_blocking=True)
+            lp.opt.step(x_dev, ref_dev, xpp, first_step=(i == 0), u0_out=u_dev)
+            u_host.copy_(u_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()              # the caller needs u0 on the host every step
+
+        for i in range(a.warmup):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(a.warmup, a.warmup + a.steps):
+            e2e_step(i)
+        g1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        te = torch.tensor([max(g0.elapsed_time(g1), wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * a.steps / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": B * (13 + N * 13) * 8, "d2h_bytes_per_step": B * 4 * 8,
+               "ms_per_step": float(te.item()) / a.steps,
+               "note": "per step: pinned-host x_now [B,13] + reference chunk [B,N,13] -> device, quad_optimizer.step, "
+                       "u0 [B,4] -> pinned host, stream sync; states replayed from a recorded closed loop"}
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle as orc
+        nthreads = orc.max_threads()
+        Bs = a.cpu_sample_vehicles or 4 * nthreads
+        v, el, _ = cpu_closed_loop(a, traj_np[:Bs], x0_np[:Bs], 5, nthreads)          # calibrate
+        steps_cpu = int(max(5, min(200, 15.0 * v / Bs)))
+        v, el, it_cpu = cpu_closed_loop(a, traj_np[:Bs], x0_np[:Bs], steps_cpu, nthreads)
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": f"first {Bs} vehicles x {steps_cpu} steps of the same workload, {el:.1f} s, C oracle with OpenMP over vehicles "
+                         f"(exact QP: IPM to 1e-13 + active-set polish, mean {it_cpu:.1f} IPM iterations)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f%d" % a.precision, "data": "synthetic", "config": workload_config(a, world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
+                "solver": {"status_not_ok_last_step": bad, "ipm_iters_mean": n_ipm_mean}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)

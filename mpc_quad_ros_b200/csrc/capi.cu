@@ -1,0 +1,582 @@
+// capi.cu — C-ABI of libqmpc.so (include/qmpc.h): handle management and kernel launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC capi.cu -o libqmpc.so
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/qmpc.h"
+#include "aux_kernels.cuh"
+#include "host_params.h"
+#include "mpc_kernels.cuh"
+#include "rgp_kernels.cuh"
+
+using namespace qmpc;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(QMPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                                 \
+    do {                                                                                               \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+        cudaError_t e_ = cudaGetLastError();                                                           \
+        if (e_ != cudaSuccess) return fail(QMPC_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
+
+constexpr int IPM_WARPS = 4;
+constexpr int RGP_WARPS = 4;
+
+}  // namespace
+
+struct qmpc_solver {
+    qmpc_config cfg;
+    double dt;
+    size_t rsz;                       // sizeof(real)
+    double *x0 = nullptr, *yref = nullptr, *yref_e = nullptr, *alpha = nullptr, *xit = nullptr, *uit = nullptr;
+    double *u0 = nullptr, *cost = nullptr, *gpX = nullptr, *xt = nullptr, *yt = nullptr;
+    int *status = nullptr, *iters = nullptr;
+    void *W = nullptr, *fac = nullptr;
+    const double* x0_src = nullptr;   // where the next solve reads x0 / alpha from (own buffers or bound ones)
+    const double* alpha_src = nullptr;
+    int alpha_stride = 0;
+    ModelParams<double> mp64;
+    bool timing = false;              // cudaEvents around the two solve kernels (bench roofline leg only)
+    std::vector<cudaEvent_t> ev;      // triples: before linearize, before ipm, after ipm
+};
+
+struct qrgp_model {
+    int B, M, device;
+    double *X = nullptr, *theta = nullptr, *Kx = nullptr, *Kx_inv = nullptr;
+    double *mu = nullptr, *C = nullptr, *alpha = nullptr, *xt = nullptr, *yt = nullptr;
+};
+
+extern "C" {
+
+const char* qmpc_last_error(void) { return g_err.c_str(); }
+int qmpc_version(void) { return 100; }
+long long qmpc_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------- solver
+
+int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
+{
+    if (!cfg || !out) return fail(QMPC_ERR_ARG, "null argument");
+    if (cfg->batch < 1 || cfg->n_nodes < 1 || cfg->n_nodes > 256) return fail(QMPC_ERR_ARG, "batch/n_nodes out of range");
+    if (cfg->n_basis < 0 || cfg->n_basis > 128) return fail(QMPC_ERR_ARG, "n_basis must be in [0,128]");
+    if (cfg->precision != 64 && cfg->precision != 32 && cfg->precision != 0) return fail(QMPC_ERR_ARG, "precision must be 64 or 32");
+    if (cfg->n_basis > 0 && !cfg->gp_X) return fail(QMPC_ERR_ARG, "gp_X is NULL with n_basis > 0");
+    if (!(cfg->t_horizon > 0) || !(cfg->ubu > cfg->lbu)) return fail(QMPC_ERR_ARG, "t_horizon / bounds invalid");
+    CU_TRY(cudaSetDevice(cfg->device));
+    qmpc_solver* h = new qmpc_solver();
+    h->cfg = *cfg;
+    if (h->cfg.precision == 0) h->cfg.precision = 64;
+    h->cfg.gp_X = nullptr;
+    h->dt = cfg_dt(*cfg);
+    h->rsz = h->cfg.precision == 64 ? 8 : 4;
+    const size_t B = cfg->batch, N = cfg->n_nodes, M = cfg->n_basis;
+    fill_model(*cfg, h->mp64);
+#define ALLOC(p, n) CU_TRY(cudaMalloc(reinterpret_cast<void**>(&(p)), (n)))
+    ALLOC(h->x0, B * NX * 8); ALLOC(h->yref, B * N * NY * 8); ALLOC(h->yref_e, B * NX * 8);
+    ALLOC(h->alpha, B * 3 * (M ? M : 1) * 8); ALLOC(h->xit, B * (N + 1) * NX * 8); ALLOC(h->uit, B * N * NU * 8);
+    ALLOC(h->u0, B * NU * 8); ALLOC(h->cost, B * 8); ALLOC(h->status, B * 4); ALLOC(h->iters, B * 4);
+    ALLOC(h->xt, B * 3 * 8); ALLOC(h->yt, B * 3 * 8);
+    ALLOC(h->W, B * N * WT * h->rsz); ALLOC(h->fac, B * N * FAC * h->rsz);
+    ALLOC(h->gpX, 3 * (M ? M : 1) * 8);
+#undef ALLOC
+    CU_TRY(cudaMemset(h->x0, 0, B * NX * 8)); CU_TRY(cudaMemset(h->yref, 0, B * N * NY * 8));
+    CU_TRY(cudaMemset(h->yref_e, 0, B * NX * 8)); CU_TRY(cudaMemset(h->alpha, 0, B * 3 * (M ? M : 1) * 8));
+    CU_TRY(cudaMemset(h->xit, 0, B * (N + 1) * NX * 8)); CU_TRY(cudaMemset(h->uit, 0, B * N * NU * 8));
+    CU_TRY(cudaMemset(h->u0, 0, B * NU * 8)); CU_TRY(cudaMemset(h->cost, 0, B * 8));
+    CU_TRY(cudaMemset(h->status, 0, B * 4)); CU_TRY(cudaMemset(h->iters, 0, B * 4));
+    if (M) CU_TRY(cudaMemcpy(h->gpX, cfg->gp_X, 3 * M * 8, cudaMemcpyHostToDevice));
+    h->x0_src = h->x0; h->alpha_src = h->alpha; h->alpha_stride = 3 * (int)M;
+    const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N) * 8, smem32 = smem64 / 2;
+    if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
+    CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+    CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+    CU_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return QMPC_OK;
+}
+
+int qmpc_destroy(qmpc_handle_t h)
+{
+    if (!h) return QMPC_OK;
+    cudaSetDevice(h->cfg.device);
+    void* ps[] = {h->x0, h->yref, h->yref_e, h->alpha, h->xit, h->uit, h->u0, h->cost, h->status, h->iters,
+                  h->W, h->fac, h->gpX, h->xt, h->yt};
+    for (void* p : ps) if (p) cudaFree(p);
+    delete h;
+    return QMPC_OK;
+}
+
+static int copy_dd(void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (!dst || !src) return fail(QMPC_ERR_ARG, "null pointer");
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+    return QMPC_OK;
+}
+
+int qmpc_set_yref(qmpc_handle_t h, const double* yref, const double* yref_e, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    const size_t B = h->cfg.batch, N = h->cfg.n_nodes;
+    int rc = copy_dd(h->yref, yref, B * N * NY * 8, stream);
+    if (rc) return rc;
+    return copy_dd(h->yref_e, yref_e, B * NX * 8, stream);
+}
+
+int qmpc_set_reference(qmpc_handle_t h, const double* x_ref, const double* u_ref, void* stream)
+{
+    if (!h || !x_ref) return fail(QMPC_ERR_ARG, "null argument");
+    const int B = h->cfg.batch, N = h->cfg.n_nodes;
+    set_reference_kernel<<<cdiv((long long)B * N * NY, 256), 256, 0, S(stream)>>>(B, N, x_ref, u_ref, 0.16, h->yref, h->yref_e);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qmpc_set_x0(qmpc_handle_t h, const double* x0, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    h->x0_src = h->x0;
+    return copy_dd(h->x0, x0, (size_t)h->cfg.batch * NX * 8, stream);
+}
+
+int qmpc_set_params(qmpc_handle_t h, const double* mu, const double* Kx_inv, void* stream)
+{
+    if (!h || !mu || !Kx_inv) return fail(QMPC_ERR_ARG, "null argument");
+    const int B = h->cfg.batch, M = h->cfg.n_basis;
+    if (M == 0) return fail(QMPC_ERR_ARG, "solver was created without an RGP model (n_basis == 0)");
+    qrgp_alpha_kernel<<<cdiv((long long)B * 3 * M, 128), 128, 0, S(stream)>>>(B, M, Kx_inv, mu, h->alpha);
+    LAUNCH_CHECK();
+    h->alpha_src = h->alpha; h->alpha_stride = 3 * M;
+    return QMPC_OK;
+}
+
+int qmpc_set_alpha(qmpc_handle_t h, const double* alpha, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    if (h->cfg.n_basis == 0) return fail(QMPC_ERR_ARG, "solver was created without an RGP model (n_basis == 0)");
+    h->alpha_src = h->alpha; h->alpha_stride = 3 * h->cfg.n_basis;
+    return copy_dd(h->alpha, alpha, (size_t)h->cfg.batch * 3 * h->cfg.n_basis * 8, stream);
+}
+
+int qmpc_set_iterate(qmpc_handle_t h, const double* x, const double* u, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    const size_t B = h->cfg.batch, N = h->cfg.n_nodes;
+    int rc = copy_dd(h->xit, x, B * (N + 1) * NX * 8, stream);
+    if (rc) return rc;
+    return copy_dd(h->uit, u, B * N * NU * 8, stream);
+}
+
+int qmpc_get_iterate(qmpc_handle_t h, double* x, double* u, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    const size_t B = h->cfg.batch, N = h->cfg.n_nodes;
+    int rc = copy_dd(x, h->xit, B * (N + 1) * NX * 8, stream);
+    if (rc) return rc;
+    return copy_dd(u, h->uit, B * N * NU * 8, stream);
+}
+
+}  // extern "C"
+
+template <typename real>
+static int solve_impl(qmpc_solver* h, void* stream)
+{
+    const int B = h->cfg.batch, N = h->cfg.n_nodes;
+    LinArgs<real> la;
+    fill_lin_args(h->cfg, la);
+    la.xit = h->xit; la.uit = h->uit; la.yref = h->yref; la.alpha = h->alpha_src; la.alpha_stride = h->alpha_stride;
+    la.gpX = h->gpX; la.W = static_cast<real*>(h->W);
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (h->timing && h->ev.size() < 3 * 8192) {
+        CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1)); CU_TRY(cudaEventCreate(&e2));
+        h->ev.push_back(e0); h->ev.push_back(e1); h->ev.push_back(e2);
+        CU_TRY(cudaEventRecord(e0, S(stream)));
+    }
+    qmpc_linearize_kernel<real><<<cdiv((long long)B * N * 16, 128), 128, 0, S(stream)>>>(la);
+    LAUNCH_CHECK();
+    if (e1) CU_TRY(cudaEventRecord(e1, S(stream)));
+    IpmArgs<real> ia;
+    fill_ipm_args(h->cfg, ia);
+    ia.x0 = h->x0_src; ia.yref = h->yref; ia.yref_e = h->yref_e; ia.xit = h->xit; ia.uit = h->uit;
+    ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
+    ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters;
+    const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real);
+    qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
+    LAUNCH_CHECK();
+    if (e2) CU_TRY(cudaEventRecord(e2, S(stream)));
+    return QMPC_OK;
+}
+
+extern "C" {
+
+int qmpc_solve(qmpc_handle_t h, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    return h->cfg.precision == 64 ? solve_impl<double>(h, stream) : solve_impl<float>(h, stream);
+}
+
+int qmpc_get_u0(qmpc_handle_t h, double* u0, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(u0, h->u0, (size_t)h->cfg.batch * NU * 8, stream);
+}
+int qmpc_get_x(qmpc_handle_t h, double* x, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(x, h->xit, (size_t)h->cfg.batch * (h->cfg.n_nodes + 1) * NX * 8, stream);
+}
+int qmpc_get_u(qmpc_handle_t h, double* u, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(u, h->uit, (size_t)h->cfg.batch * h->cfg.n_nodes * NU * 8, stream);
+}
+int qmpc_get_cost(qmpc_handle_t h, double* cost, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(cost, h->cost, (size_t)h->cfg.batch * 8, stream);
+}
+int qmpc_get_status(qmpc_handle_t h, int* status, int* iters, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    if (status) { int rc = copy_dd(status, h->status, (size_t)h->cfg.batch * 4, stream); if (rc) return rc; }
+    if (iters) { int rc = copy_dd(iters, h->iters, (size_t)h->cfg.batch * 4, stream); if (rc) return rc; }
+    return QMPC_OK;
+}
+int qmpc_iters_total(qmpc_handle_t h, long long* total, void* stream)
+{
+    if (!h || !total) return fail(QMPC_ERR_ARG, "null argument");
+    std::vector<int> it(h->cfg.batch);
+    CU_TRY(cudaMemcpyAsync(it.data(), h->iters, it.size() * 4, cudaMemcpyDeviceToHost, S(stream)));
+    CU_TRY(cudaStreamSynchronize(S(stream)));
+    long long s = 0;
+    for (int v : it) s += v;
+    *total = s;
+    return QMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+
+static void model_from_quad(const double* quad, ModelParams<double>& mp)
+{
+    qmpc_config c;
+    std::memset(&c, 0, sizeof(c));
+    std::memcpy(c.quad, quad, sizeof(c.quad));
+    fill_model(c, mp);
+    mp.M = 0;
+}
+
+int qmpc_predict_nominal(const double* quad, int B, const double* x, const double* u, double dt, int body_frame,
+                         double* x_next, void* stream)
+{
+    if (!quad || !x || !u || !x_next || B < 1) return fail(QMPC_ERR_ARG, "bad argument");
+    ModelParams<double> mp;
+    model_from_quad(quad, mp);
+    predict_nominal_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(mp, B, x, u, dt, body_frame, x_next);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qmpc_compute_a_drag(int B, const double* x_now, const double* x_pred, double dt, double* v_body, double* a_drag,
+                        void* stream)
+{
+    if (!x_now || !x_pred || !v_body || !a_drag || B < 1) return fail(QMPC_ERR_ARG, "bad argument");
+    compute_a_drag_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(B, x_now, x_pred, dt, v_body, a_drag);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qmpc_reference_chunk(int B, int K, const double* traj, int idx, int N, int skip, double* chunk, void* stream)
+{
+    if (!traj || !chunk || B < 1 || K < 1 || N < 1 || skip < 1 || idx < 0) return fail(QMPC_ERR_ARG, "bad argument");
+    reference_chunk_kernel<<<cdiv((long long)B * N * NX, 256), 256, 0, S(stream)>>>(B, K, traj, idx, N, skip, chunk);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qmpc_plant_period(const double* quad, const double* plant, int B, double* x, const double* u, double sim_dt,
+                      int n_sub, void* stream)
+{
+    if (!quad || !plant || !x || !u || B < 1 || n_sub < 0) return fail(QMPC_ERR_ARG, "bad argument");
+    ModelParams<double> mp;
+    model_from_quad(quad, mp);
+    PlantParams pp;
+    pp.aero = plant[0]; pp.rotor[0] = plant[1]; pp.rotor[1] = plant[2]; pp.rotor[2] = plant[3]; pp.mass = quad[0];
+    plant_period_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(mp, pp, B, x, u, sim_dt, n_sub);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- RGP
+
+int qrgp_create(int batch, int n_basis, const double* X, const double* theta, const double* Kx, const double* Kx_inv,
+                int device, qrgp_handle_t* out)
+{
+    if (!X || !theta || !Kx || !Kx_inv || !out) return fail(QMPC_ERR_ARG, "null argument");
+    if (batch < 1 || n_basis < 1 || n_basis > 32 * RGP_MAXT) return fail(QMPC_ERR_ARG, "batch/n_basis out of range");
+    CU_TRY(cudaSetDevice(device));
+    qrgp_model* g = new qrgp_model();
+    g->B = batch; g->M = n_basis; g->device = device;
+    const size_t B = batch, M = n_basis;
+#define ALLOC(p, n) CU_TRY(cudaMalloc(reinterpret_cast<void**>(&(p)), (n)))
+    ALLOC(g->X, 3 * M * 8); ALLOC(g->theta, 9 * 8); ALLOC(g->Kx, 3 * M * M * 8); ALLOC(g->Kx_inv, 3 * M * M * 8);
+    ALLOC(g->mu, B * 3 * M * 8); ALLOC(g->C, B * 3 * M * M * 8); ALLOC(g->alpha, B * 3 * M * 8);
+    ALLOC(g->xt, B * 3 * 8); ALLOC(g->yt, B * 3 * 8);
+#undef ALLOC
+    CU_TRY(cudaMemcpy(g->X, X, 3 * M * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g->theta, theta, 9 * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g->Kx, Kx, 3 * M * M * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g->Kx_inv, Kx_inv, 3 * M * M * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemset(g->mu, 0, B * 3 * M * 8));
+    CU_TRY(cudaMemset(g->alpha, 0, B * 3 * M * 8));
+    for (size_t b = 0; b < B; ++b)   // C0 = K_x for every vehicle (RGP.py:144)
+        CU_TRY(cudaMemcpyAsync(g->C + b * 3 * M * M, g->Kx, 3 * M * M * 8, cudaMemcpyDeviceToDevice, 0));
+    CU_TRY(cudaDeviceSynchronize());
+    *out = g;
+    return QMPC_OK;
+}
+
+int qrgp_destroy(qrgp_handle_t g)
+{
+    if (!g) return QMPC_OK;
+    cudaSetDevice(g->device);
+    void* ps[] = {g->X, g->theta, g->Kx, g->Kx_inv, g->mu, g->C, g->alpha, g->xt, g->yt};
+    for (void* p : ps) if (p) cudaFree(p);
+    delete g;
+    return QMPC_OK;
+}
+
+static int regress_launch(qrgp_model* g, const double* xt, const double* yt, void* stream)
+{
+    RgpArgs a;
+    a.B = g->B; a.M = g->M; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.mu = g->mu; a.C = g->C;
+    a.alpha = g->alpha; a.xt = xt; a.yt = yt;
+    const size_t smem = (size_t)RGP_WARPS * 3 * g->M * 8;
+    qrgp_regress_kernel<RGP_WARPS><<<cdiv((long long)g->B * 3, RGP_WARPS), RGP_WARPS * 32, smem, S(stream)>>>(a);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qrgp_regress(qrgp_handle_t g, const double* xt, const double* yt, void* stream)
+{
+    if (!g || !xt || !yt) return fail(QMPC_ERR_ARG, "null argument");
+    return regress_launch(g, xt, yt, stream);
+}
+
+int qrgp_regress_from_states(qrgp_handle_t g, const double* x_now, const double* x_pred_prev, double dt,
+                             double* v_body, double* a_drag, void* stream)
+{
+    if (!g || !x_now || !x_pred_prev) return fail(QMPC_ERR_ARG, "null argument");
+    compute_a_drag_kernel<<<cdiv(g->B, 128), 128, 0, S(stream)>>>(g->B, x_now, x_pred_prev, dt, g->xt, g->yt);
+    LAUNCH_CHECK();
+    if (v_body) { int rc = copy_dd(v_body, g->xt, (size_t)g->B * 3 * 8, stream); if (rc) return rc; }
+    if (a_drag) { int rc = copy_dd(a_drag, g->yt, (size_t)g->B * 3 * 8, stream); if (rc) return rc; }
+    return regress_launch(g, g->xt, g->yt, stream);
+}
+
+int qrgp_get_mu(qrgp_handle_t g, double* mu, void* stream)
+{
+    if (!g) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(mu, g->mu, (size_t)g->B * 3 * g->M * 8, stream);
+}
+int qrgp_get_C(qrgp_handle_t g, double* C, void* stream)
+{
+    if (!g) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(C, g->C, (size_t)g->B * 3 * g->M * g->M * 8, stream);
+}
+int qrgp_get_alpha(qrgp_handle_t g, double* alpha, void* stream)
+{
+    if (!g) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(alpha, g->alpha, (size_t)g->B * 3 * g->M * 8, stream);
+}
+int qrgp_set_state(qrgp_handle_t g, const double* mu, const double* C, void* stream)
+{
+    if (!g) return fail(QMPC_ERR_ARG, "null handle");
+    if (mu) {
+        int rc = copy_dd(g->mu, mu, (size_t)g->B * 3 * g->M * 8, stream);
+        if (rc) return rc;
+        qrgp_alpha_kernel<<<cdiv((long long)g->B * 3 * g->M, 128), 128, 0, S(stream)>>>(g->B, g->M, g->Kx_inv, g->mu, g->alpha);
+        LAUNCH_CHECK();
+    }
+    if (C) return copy_dd(g->C, C, (size_t)g->B * 3 * g->M * g->M * 8, stream);
+    return QMPC_OK;
+}
+const double* qrgp_Kx_inv_device(qrgp_handle_t g) { return g ? g->Kx_inv : nullptr; }
+const double* qrgp_mu_device(qrgp_handle_t g) { return g ? g->mu : nullptr; }
+
+static int predict_launch(qrgp_model* g, int m, const double* xs, const double* mu, const double* C, double* mean,
+                          double* var, void* stream)
+{
+    RgpPredArgs a;
+    a.B = g->B; a.M = g->M; a.m = m; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.mu = mu; a.C = C;
+    a.xs = xs; a.mean = mean; a.var = var;
+    const size_t smem = (size_t)RGP_WARPS * 2 * g->M * 8;
+    qrgp_predict_kernel<RGP_WARPS><<<cdiv((long long)g->B * 3, RGP_WARPS), RGP_WARPS * 32, smem, S(stream)>>>(a);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qrgp_predict(qrgp_handle_t g, int m, const double* xs, double* mean, double* var, void* stream)
+{
+    if (!g || !xs || !mean || m < 1) return fail(QMPC_ERR_ARG, "bad argument");
+    return predict_launch(g, m, xs, g->mu, g->C, mean, var, stream);
+}
+
+int qrgp_predict_using_y(qrgp_handle_t g, int m, const double* xs, const double* y, double* mean, void* stream)
+{
+    if (!g || !xs || !y || !mean || m < 1) return fail(QMPC_ERR_ARG, "bad argument");
+    return predict_launch(g, m, xs, y, nullptr, mean, nullptr, stream);
+}
+
+int qrgp_shared_accumulate(qrgp_handle_t g, int B, const double* xt, const double* yt, double* info, void* stream)
+{
+    if (!g || !xt || !yt || !info || B < 1) return fail(QMPC_ERR_ARG, "bad argument");
+    const int M = g->M;
+    const size_t per_warp = (size_t)(M * M + 3 * M) * 8;
+    int warps = int((200 * 1024) / per_warp);
+    warps = warps > 8 ? 8 : warps;
+    if (warps < 1) return fail(QMPC_ERR_ARG, "n_basis too large for the shared accumulate tile");
+    RgpSharedArgs a;
+    a.B = B; a.M = M; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.xt = xt; a.yt = yt; a.info = info;
+    CU_TRY(cudaMemsetAsync(info, 0, (size_t)3 * (M * M + M) * 8, S(stream)));
+    int blocks = cdiv(B, warps * 8);
+    blocks = blocks > 148 ? 148 : blocks;
+    dim3 grid(blocks, 3);
+    const size_t smem = per_warp * warps;
+#define SHARED_LAUNCH(W)                                                                                         \
+    case W:                                                                                                      \
+        CU_TRY(cudaFuncSetAttribute(qrgp_shared_accumulate_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        qrgp_shared_accumulate_kernel<W><<<grid, W * 32, smem, S(stream)>>>(a);                                  \
+        break;
+    switch (warps) {
+        SHARED_LAUNCH(1) SHARED_LAUNCH(2) SHARED_LAUNCH(3) SHARED_LAUNCH(4)
+        SHARED_LAUNCH(5) SHARED_LAUNCH(6) SHARED_LAUNCH(7) SHARED_LAUNCH(8)
+    }
+#undef SHARED_LAUNCH
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qrgp_shared_apply(qrgp_handle_t g, const double* info, void* stream)
+{
+    if (!g || !info) return fail(QMPC_ERR_ARG, "null argument");
+    if (g->B != 1) return fail(QMPC_ERR_ARG, "shared model handles must be created with batch == 1");
+    const int M = g->M;
+    const size_t smem = (size_t)M * (2 * M + 1) * 8;
+    if (smem > 220 * 1024) return fail(QMPC_ERR_ARG, "n_basis too large for the shared apply tile");
+    CU_TRY(cudaFuncSetAttribute(qrgp_shared_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qrgp_shared_apply_kernel<<<3, 256, smem, S(stream)>>>(M, info, g->mu, g->C, g->Kx_inv, g->alpha);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+// --------------------------------------------------------------------------------------- fused step
+
+int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const double* x_ref, double* x_pred_prev,
+              int first_step, double* u0_out, void* stream)
+{
+    if (!h || !x_now || !x_ref || !x_pred_prev) return fail(QMPC_ERR_ARG, "null argument");
+    const int B = h->cfg.batch, N = h->cfg.n_nodes;
+    if (g && (g->M != h->cfg.n_basis || (g->B != B && g->B != 1)))
+        return fail(QMPC_ERR_ARG, "RGP handle does not match the solver (n_basis / batch)");
+    set_reference_kernel<<<cdiv((long long)B * N * NY, 256), 256, 0, S(stream)>>>(B, N, x_ref, nullptr, 0.16, h->yref, h->yref_e);
+    LAUNCH_CHECK();
+    h->x0_src = x_now;
+    if (g) { h->alpha_src = g->alpha; h->alpha_stride = g->B == 1 ? 0 : 3 * g->M; }
+    int rc = qmpc_solve(h, stream);
+    h->x0_src = h->x0;
+    if (g) { h->alpha_src = h->alpha; h->alpha_stride = 3 * h->cfg.n_basis; }
+    if (rc) return rc;
+    const bool per_vehicle = g && g->B == B;
+    double* xt = per_vehicle ? g->xt : h->xt;
+    double* yt = per_vehicle ? g->yt : h->yt;
+    post_solve_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(h->mp64, B, h->dt, first_step, x_now, h->u0, x_pred_prev,
+                                                           g ? xt : nullptr, g ? yt : nullptr);
+    LAUNCH_CHECK();
+    if (per_vehicle) { rc = regress_launch(g, xt, yt, stream); if (rc) return rc; }
+    if (u0_out) return copy_dd(u0_out, h->u0, (size_t)B * NU * 8, stream);
+    return QMPC_OK;
+}
+
+/* kernel timing for the roofline leg of bench.py: enable, run solves, then read (synchronises the device).
+ * ms_lin / ms_ipm = summed device time of the linearize / ipm launches since enabling; count = solves timed. */
+int qmpc_timing_enable(qmpc_handle_t h, int on)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    h->ev.clear();
+    h->timing = on != 0;
+    return QMPC_OK;
+}
+int qmpc_timing_read(qmpc_handle_t h, double* ms_lin, double* ms_ipm, int* count)
+{
+    if (!h || !ms_lin || !ms_ipm || !count) return fail(QMPC_ERR_ARG, "null argument");
+    CU_TRY(cudaDeviceSynchronize());
+    double a = 0, b = 0;
+    for (size_t i = 0; i + 2 < h->ev.size(); i += 3) {
+        float t1 = 0, t2 = 0;
+        CU_TRY(cudaEventElapsedTime(&t1, h->ev[i], h->ev[i + 1]));
+        CU_TRY(cudaEventElapsedTime(&t2, h->ev[i + 1], h->ev[i + 2]));
+        a += t1; b += t2;
+    }
+    *ms_lin = a; *ms_ipm = b; *count = int(h->ev.size() / 3);
+    return QMPC_OK;
+}
+
+/* register-resident FMA microbenchmark: measured non-tensor FMA peak of this GPU (TFLOP/s), precision 64 or 32 */
+int qmpc_fma_peak(int precision, double* tflops, void* stream)
+{
+    if (!tflops || (precision != 64 && precision != 32)) return fail(QMPC_ERR_ARG, "bad argument");
+    int dev = 0, sms = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double* sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_TRY(cudaEventRecord(e0, S(stream)));
+        if (precision == 64) fma_peak_kernel<double><<<blocks, threads, 0, S(stream)>>>(iters, sink);
+        else fma_peak_kernel<float><<<blocks, threads, 0, S(stream)>>>(iters, sink);
+        LAUNCH_CHECK();
+        CU_TRY(cudaEventRecord(e1, S(stream)));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = 2.0 * 16.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return QMPC_OK;
+}
+
+/* residual buffers written by qmpc_step (v_body, a_drag of the last step), for the shared-swarm exchange */
+const double* qmpc_residual_x_device(qmpc_handle_t h) { return h ? h->xt : nullptr; }
+const double* qmpc_residual_y_device(qmpc_handle_t h) { return h ? h->yt : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// host_params.h — host-side translation of qmpc_config into kernel argument blocks
+// (shared by capi.cu and the test-only emulation harness).
+#pragma once
+#include "../../include/qmpc.h"
+#include "mpc_kernels.cuh"
+
+namespace qmpc {
+
+typedef qmpc_config HostOcp;
+
+template <typename real>
+inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
+{
+    const double* q = c.quad;
+    const double mass = q[0], T = q[1];
+    const double* J = q + 2;
+    mp.thrust_over_mass = real(T / mass);
+    mp.T = real(T);
+    for (int i = 0; i < 4; ++i) { mp.xf[i] = real(q[5 + i]); mp.yf[i] = real(q[9 + i]); mp.zt[i] = real(q[13 + i]); }
+    for (int i = 0; i < 3; ++i) { mp.invJ[i] = real(1.0 / J[i]); mp.g[i] = real(q[17 + i]); }
+    mp.Jc[0] = real(J[1] - J[2]); mp.Jc[1] = real(J[2] - J[0]); mp.Jc[2] = real(J[0] - J[1]);
+    for (int d = 0; d < 3; ++d) {
+        const double L = c.gp_theta[3 * d], sf = c.gp_theta[3 * d + 1];
+        mp.sf2[d] = real(sf * sf);
+        mp.iL2[d] = real(L != 0.0 ? 1.0 / (L * L) : 0.0);
+    }
+    mp.M = c.n_basis;
+}
+
+inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
+inline int ipm_smem_reals(int N) { return SM_VEC + SM_NVEC * 4 * N + 8; }
+
+template <typename real>
+inline void fill_lin_args(const qmpc_config& c, LinArgs<real>& a)
+{
+    a.B = c.batch; a.N = c.n_nodes; a.dt = real(cfg_dt(c));
+    fill_model(c, a.mp);
+    a.alpha_stride = 3 * c.n_basis;
+    for (int i = 0; i < 13; ++i) a.Qd[i] = real(cfg_dt(c) * c.w_diag[i]);
+}
+
+template <typename real>
+inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
+{
+    const double dt = cfg_dt(c);
+    a.B = c.batch; a.N = c.n_nodes;
+    for (int i = 0; i < 13; ++i) { a.Qd[i] = real(dt * c.w_diag[i]); a.QNd[i] = real(c.we_diag[i]); }
+    for (int i = 0; i < 4; ++i) a.Rd[i] = real(dt * c.w_diag[13 + i]);
+    a.dt = real(dt); a.lb = real(c.lbu); a.ub = real(c.ubu);
+    const bool f64 = sizeof(real) == 8;
+    a.mu_tol = real(c.ipm_mu_tol > 0 ? c.ipm_mu_tol : (f64 ? 1e-13 : 1e-6));
+    a.max_iter = c.ipm_max_iter > 0 ? c.ipm_max_iter : 50;
+    a.smem_per_warp = ipm_smem_reals(c.n_nodes);
+}
+
+}  // namespace qmpc

@@ -1,0 +1,580 @@
+// mpc_kernels.cuh — the two kernels behind qmpc_solve (one SQP-RTI iteration per vehicle).
+//
+//   K1  qmpc_linearize_kernel : RK4 + forward sensitivities (incl. GP Jacobian) at the N nodes of every
+//       vehicle.  16 lanes per node, one sensitivity column per lane.  Replaces CasADi expl_vde_forw +
+//       acados ERK inside AcadosOcpSolver.solve() (reference src/quad_opt.py:333, model :164-262).
+//   K2  qmpc_ipm_kernel       : Gauss-Newton QP (LINEAR_LS cost scaled by dt, x0 pinned, box on u) solved by a
+//       Mehrotra predictor-corrector IPM whose Newton systems are Riccati recursions; one OCP per warp.
+//       Replaces acados SQP_RTI + full condensing + HPIPM (reference src/quad_opt.py:146-151,333;
+//       src/_acados_ocp.json:2082-2110).  Full step, un-shifted persistent iterate, objective at the new
+//       iterate.
+//
+// Per-stage tile written by K1 and streamed by K2 (HBM/L2, `real`):   W[13 rows][16 cols]
+//   cols 0..3  = B = dPhi/du            cols 4..13 = dPhi/dx_s for s = 3..12 (q,v,r)
+//   col 14     = b = Phi(x_k,u_k) - x_{k+1}  (QP in increments)        col 15 = q = dt*W_x (x_k - xref_k)
+// The three position columns of A are unit vectors (f does not depend on p) and are never stored.
+#pragma once
+#include "common.cuh"
+#include "model.cuh"
+
+namespace qmpc {
+
+constexpr int QMPC_STATUS_OK_ = 0, QMPC_STATUS_MAXITER_ = 1, QMPC_STATUS_NAN_ = 2;
+constexpr int WT = 13 * 16;  // reals per stage tile
+constexpr int FAC = 72;      // reals per stage factor record: Lx[13][4], lg[4], Lam[10], lgc[4], pad[2]
+
+template <typename real>
+struct LinArgs {
+    int B, N;
+    real dt;
+    ModelParams<real> mp;
+    real Qd[13];          // dt * w_diag[0:13]
+    const double* xit;    // [B][N+1][13]
+    const double* uit;    // [B][N][4]
+    const double* yref;   // [B][N][17]
+    const double* alpha;  // [B][3][M]  (unused when mp.M == 0)
+    int alpha_stride;     // doubles between vehicles: 3*M, or 0 when one shared model serves every vehicle
+    const double* gpX;    // [3][M]
+    real* W;              // [B][N][13][16]
+};
+
+// GP mean/slope per body axis; the 3*M kernel evaluations are spread over the 16 lanes of the group.
+template <typename real>
+__device__ __forceinline__ void gp_group_eval(const ModelParams<real>& mp, unsigned hmask, int j,
+                                              const double* __restrict__ gpX, const double* __restrict__ alpha,
+                                              const real* vb, real* mu, real* dmu)
+{
+    real s0 = 0, s1 = 0, s2 = 0, d0 = 0, d1 = 0, d2 = 0;
+    const int M = mp.M, tot = 3 * M;
+    for (int p = j; p < tot; p += 16) {
+        const int d = p / M;
+        const real v = d == 0 ? vb[0] : (d == 1 ? vb[1] : vb[2]);
+        const real il2 = d == 0 ? mp.iL2[0] : (d == 1 ? mp.iL2[1] : mp.iL2[2]);
+        const real sf2 = d == 0 ? mp.sf2[0] : (d == 1 ? mp.sf2[1] : mp.sf2[2]);
+        const real e = v - real(__ldg(gpX + p));
+        const real ka = sf2 * rexp<real>(real(-0.5) * e * il2 * e) * real(__ldg(alpha + p));
+        const real dk = ka * (-e * il2);
+        if (d == 0) { s0 += ka; d0 += dk; } else if (d == 1) { s1 += ka; d1 += dk; } else { s2 += ka; d2 += dk; }
+    }
+    mu[0] = half_sum(hmask, s0); mu[1] = half_sum(hmask, s1); mu[2] = half_sum(hmask, s2);
+    dmu[0] = half_sum(hmask, d0); dmu[1] = half_sum(hmask, d1); dmu[2] = half_sum(hmask, d2);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(128) qmpc_linearize_kernel(LinArgs<real> a)
+{
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int node = gt >> 4, j = gt & 15;
+    if (node >= a.B * a.N) return;                     // whole 16-lane group leaves together
+    const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+    const int b = node / a.N, k = node - b * a.N;
+    const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
+    const double* uk = a.uit + ((size_t)b * a.N + k) * NU;
+    const double* al = a.alpha + (size_t)b * a.alpha_stride;
+    real x[NX], u[NU], du[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = real(__ldg(xk + i));
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { u[i] = real(__ldg(uk + i)); du[i] = (i == j) ? real(1) : real(0); }
+    const int sj = (j >= 4 && j < 14) ? j - 1 : -1;    // state index of this lane's x-direction
+    real kprev[NX], dkprev[NX], accx[NX], accd[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { kprev[i] = 0; dkprev[i] = 0; accx[i] = x[i]; accd[i] = (i == sj) ? real(1) : real(0); }
+    const real zero3[3] = {0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
+        const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
+        real xs[NX], dxs[NX], kk[NX], dk[NX], mu[3], dmu[3];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { xs[i] = x[i] + as * kprev[i]; dxs[i] = ((i == sj) ? real(1) : real(0)) + as * dkprev[i]; }
+        if (a.mp.M > 0) {
+            real vb[3];
+            body_velocity(xs, vb);
+            gp_group_eval(a.mp, hmask, j, a.gpX, al, vb, mu, dmu);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { mu[i] = zero3[i]; dmu[i] = zero3[i]; }
+        }
+        EvalPoint<real> e;
+        eval_f(a.mp, xs, u, mu, dmu, e, kk);
+        jvp_f(a.mp, e, dxs, du, dk);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { accx[i] += ws * kk[i]; accd[i] += ws * dk[i]; kprev[i] = kk[i]; dkprev[i] = dk[i]; }
+    }
+    if (j == 14) {                                     // b = Phi - x_{k+1}
+#pragma unroll
+        for (int i = 0; i < NX; ++i) accd[i] = accx[i] - real(__ldg(xk + NX + i));
+    } else if (j == 15) {                              // q = dt W_x (x_k - xref_k)
+        const double* yr = a.yref + ((size_t)b * a.N + k) * NY;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) accd[i] = a.Qd[i] * (x[i] - real(__ldg(yr + i)));
+    }
+    real* Wt = a.W + (size_t)node * WT;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) Wt[i * 16 + j] = accd[i];
+}
+
+// ------------------------------------------------------------------------------------------ K2
+
+template <typename real>
+struct IpmArgs {
+    int B, N;
+    real Qd[13], QNd[13], Rd[4];   // dt*W_x, W_e, dt*W_u
+    real dt, lb, ub, mu_tol;
+    int max_iter;
+    int smem_per_warp;             // reals
+    const double* x0;              // [B][13]
+    const double* yref;            // [B][N][17]
+    const double* yref_e;          // [B][13]
+    double* xit;                   // [B][N+1][13]  in/out
+    double* uit;                   // [B][N][4]     in/out
+    const real* W;                 // [B][N][13][16]
+    real* fac;                     // [B][N][FAC]
+    double* u0;                    // [B][4]
+    double* cost;                  // [B]
+    int* status;                   // [B]
+    int* iters;                    // [B]
+};
+
+template <typename real>
+struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal
+    real l10, l20, l21, l30, l31, l32, i0, i1, i2, i3;
+    __device__ __forceinline__ void factor(const real* M /* 4x4 row-major, lower used */)
+    {
+        i0 = rrsqrt<real>(M[0]);
+        l10 = M[4] * i0; l20 = M[8] * i0; l30 = M[12] * i0;
+        i1 = rrsqrt<real>(M[5] - l10 * l10);
+        l21 = (M[9] - l20 * l10) * i1; l31 = (M[13] - l30 * l10) * i1;
+        i2 = rrsqrt<real>(M[10] - l20 * l20 - l21 * l21);
+        l32 = (M[14] - l30 * l20 - l31 * l21) * i2;
+        i3 = rrsqrt<real>(M[15] - l30 * l30 - l31 * l31 - l32 * l32);
+    }
+    __device__ __forceinline__ void fsolve(const real* v, real* z) const   // Lam z = v
+    {
+        z[0] = v[0] * i0;
+        z[1] = (v[1] - l10 * z[0]) * i1;
+        z[2] = (v[2] - l20 * z[0] - l21 * z[1]) * i2;
+        z[3] = (v[3] - l30 * z[0] - l31 * z[1] - l32 * z[2]) * i3;
+    }
+    __device__ __forceinline__ void bsolve_neg(const real* v, real* u) const   // Lam^T u = -v
+    {
+        u[3] = -v[3] * i3;
+        u[2] = (-v[2] - l32 * u[3]) * i2;
+        u[1] = (-v[1] - l21 * u[2] - l31 * u[3]) * i1;
+        u[0] = (-v[0] - l10 * u[1] - l20 * u[2] - l30 * u[3]) * i0;
+    }
+    __device__ __forceinline__ void store(real* p) const
+    {
+        p[0] = l10; p[1] = l20; p[2] = l21; p[3] = l30; p[4] = l31; p[5] = l32; p[6] = i0; p[7] = i1; p[8] = i2; p[9] = i3;
+    }
+    __device__ __forceinline__ void load(const real* p)
+    {
+        l10 = p[0]; l20 = p[1]; l21 = p[2]; l30 = p[3]; l31 = p[4]; l32 = p[5]; i0 = p[6]; i1 = p[7]; i2 = p[8]; i3 = p[9];
+    }
+};
+
+template <typename real>
+__device__ __forceinline__ real dot4(const real* a, const real* b)
+{
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+}
+
+// per-warp shared-memory carve-up (offsets in reals)
+constexpr int SM_P = 0;        // 14 x 14 (row 13 stays zero)
+constexpr int SM_PV = 200;     // 16  costate offset p
+constexpr int SM_WV = 216;     // 16  forward vector: u(4), z(10), one, zero
+constexpr int SM_XP = 232;     // 16  position part of the forward state
+constexpr int SM_HV = 248;     // 16  h = P b + p
+constexpr int SM_LS = 264;     // 64  l_j per tile column
+constexpr int SM_CS = 328;     // 32  Muu(16) Mpu(12) gu(4)
+constexpr int SM_VEC = 360;    // 11 vectors of 4N
+constexpr int SM_NVEC = 11;
+
+template <typename real>
+struct WarpCtx {
+    const IpmArgs<real>& a;
+    int lane, h, j, sidx, ocp, N, E;
+    unsigned hmask;
+    real *P, *pv, *wv, *xp, *hv, *Ls, *cs;
+    real *rt, *dR, *usol, *ua, *ucur, *ll, *lu, *ubar, *rdel, *cl, *cu;
+    const real* Wv;
+    real* facv;
+    const double *x0, *yref, *yref_e;
+    double *xit, *uit;
+
+    __device__ __forceinline__ void load_col(int k, real* w) const
+    {
+        const real* t = Wv + (size_t)k * WT + j;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) w[i] = __ldg(t + i * 16);
+    }
+
+    // backward Riccati sweep with factorisation; gradient: rt (inputs), q column (states), b column (offset)
+    __device__ void backward_full()
+    {
+        for (int idx = lane; idx < 196; idx += 32) P[idx] = 0;
+        __syncwarp();
+        if (lane < NX) {
+            P[lane * 14 + lane] = a.QNd[lane];
+            pv[lane] = a.QNd[lane] * real(xit[(size_t)N * NX + lane] - yref_e[lane]);
+        }
+        __syncwarp();
+        real w[NX], wn[NX];
+        load_col(N - 1, w);
+        const int r0 = h * 7;
+        for (int k = N - 1; k >= 0; --k) {
+            if (k > 0) load_col(k - 1, wn);
+            const real* tile = Wv + (size_t)k * WT;
+            const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
+            // y = P w  (own half of the rows), then exchange halves
+            real y[7], yf[NX];
+#pragma unroll
+            for (int ii = 0; ii < 7; ++ii) {
+                const real* pr = P + (r0 + ii) * 14;
+                real s = 0;
+#pragma unroll
+                for (int c = 0; c < NX; ++c) s += pr[c] * w[c];
+                y[ii] = s;
+            }
+#pragma unroll
+            for (int ii = 0; ii < 7; ++ii) {
+                const real yo = __shfl_xor_sync(FULL, y[ii], 16);
+                const real lo = h ? yo : y[ii], hi = h ? y[ii] : yo;
+                yf[ii] = lo;
+                if (ii < 6) yf[7 + ii] = hi;
+            }
+            if (lane == 14) {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) hv[i] = yf[i] + pv[i];
+            }
+            // M rows (dense tile columns r0..r0+6) of this lane's column
+            real m[7];
+#pragma unroll
+            for (int ii = 0; ii < 7; ++ii) {
+                const int i = r0 + ii;
+                real s = 0;
+#pragma unroll
+                for (int c = 0; c < NX; ++c) s += __ldg(tile + c * 16 + i) * yf[c];
+                if (i == j) s += (j < 4) ? (a.Rd[j] + dR[k * 4 + j]) : a.Qd[j - 1];
+                m[ii] = s;
+            }
+            __syncwarp();
+            real g = 0;
+#pragma unroll
+            for (int c = 0; c < NX; ++c) g += w[c] * hv[c];
+            g += (j < 4) ? rt[k * 4 + j] : qj;
+            if (lane < 4) {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) cs[aa * 4 + lane] = m[aa];
+#pragma unroll
+                for (int pi = 0; pi < 3; ++pi) cs[16 + pi * 4 + lane] = yf[pi];
+                cs[28 + lane] = g;
+            }
+            __syncwarp();
+            Chol4<real> L;
+            real lg[4], lp[3][4], lj[4], mu4[4];
+            {
+                real Muu[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) Muu[t] = cs[t];
+                L.factor(Muu);
+                L.fsolve(cs + 28, lg);
+#pragma unroll
+                for (int pi = 0; pi < 3; ++pi) L.fsolve(cs + 16 + pi * 4, lp[pi]);
+            }
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) mu4[aa] = __shfl_sync(FULL, m[aa], j);   // rows 0..3 live in the h=0 half
+            L.fsolve(mu4, lj);
+            real lpme[4];                       // l_p of "my" position state (lanes 0..2)
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) lpme[aa] = j == 0 ? lp[0][aa] : (j == 1 ? lp[1][aa] : lp[2][aa]);
+            if (h == 0) {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) Ls[j * 4 + aa] = lj[aa];
+            }
+            __syncwarp();
+            if (k > 0) {
+                if (j >= 4 && j < 14) {
+                    const int sj = j - 1;
+#pragma unroll
+                    for (int ii = 0; ii < 7; ++ii) {
+                        const int i = r0 + ii;
+                        if (i >= 4 && i < 14) P[(i - 1) * 14 + sj] = m[ii] - dot4(Ls + i * 4, lj);
+                    }
+                    if (h == 0) {
+#pragma unroll
+                        for (int pi = 0; pi < 3; ++pi) {
+                            const real v = yf[pi] - dot4(lp[pi], lj);
+                            P[pi * 14 + sj] = v;
+                            P[sj * 14 + pi] = v;
+                        }
+                        pv[sj] = g - dot4(lj, lg);
+                    }
+                }
+                if (lane < 3) {
+#pragma unroll
+                    for (int pi = 0; pi < 3; ++pi)
+                        P[pi * 14 + lane] += ((pi == lane) ? a.Qd[lane] : real(0)) - dot4(lp[pi], lpme);
+                    pv[lane] = hv[lane] + qj - dot4(lpme, lg);
+                }
+            }
+            if (h == 0) {
+                real* f = facv + (size_t)k * FAC;
+                if (j >= 4 && j < 14) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) f[(j - 1) * 4 + aa] = lj[aa];
+                } else if (j < 3) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) f[j * 4 + aa] = lpme[aa];
+                } else if (j == 14) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) f[52 + aa] = lg[aa];
+                } else if (j == 15) {
+                    L.store(f + 56);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NX; ++i) w[i] = wn[i];
+        }
+    }
+
+    // backward sweep of the gradient only (corrector): zero offset/terminal, input gradient rt
+    __device__ void backward_vec()
+    {
+        if (lane < 16) pv[lane] = 0;
+        __syncwarp();
+        real w[NX], wn[NX];
+        load_col(N - 1, w);
+        for (int k = N - 1; k >= 0; --k) {
+            if (k > 0) load_col(k - 1, wn);
+            const real* f = facv + (size_t)k * FAC;
+            Chol4<real> L;
+            L.load(f + 56);
+            real lx[4] = {0, 0, 0, 0};
+            if (sidx >= 0) {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) lx[aa] = f[sidx * 4 + aa];
+            }
+            real g = 0;
+#pragma unroll
+            for (int c = 0; c < NX; ++c) g += w[c] * pv[c];
+            if (j < 4) g += rt[k * 4 + j];
+            real gu[4], lgc[4];
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) gu[aa] = __shfl_sync(FULL, g, aa);
+            L.fsolve(gu, lgc);
+            const real pold = j < 3 ? pv[j] : real(0);
+            __syncwarp();
+            if (h == 0) {
+                if (j >= 4 && j < 14) pv[j - 1] = g - dot4(lx, lgc);
+                else if (j < 3) pv[j] = pold - dot4(lx, lgc);
+                else if (j == 14) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) facv[(size_t)k * FAC + 66 + aa] = lgc[aa];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NX; ++i) w[i] = wn[i];
+        }
+    }
+
+    // forward sweep.  MODE 0: feedback with lg and offset b (predictor, writes usol)
+    //                 MODE 1: feedback with lgc, homogeneous (corrector increment, writes usol)
+    //                 MODE 2: open loop with usol, offset b; writes the new iterate and returns the objective
+    template <int MODE>
+    __device__ real forward()
+    {
+        if (lane < NX) {
+            const real v = MODE == 1 ? real(0) : real(x0[lane] - xit[lane]);
+            if (lane < 3) xp[lane] = v; else wv[lane + 1] = v;
+        } else if (lane == 14) wv[14] = MODE == 1 ? real(0) : real(1);
+        else if (lane == 15) wv[15] = 0;
+        real cost = 0;
+        if (MODE == 2 && h == 0 && j < NX) {
+            const real e0 = real(x0[j] - yref[j]);
+            cost = real(0.5) * a.Qd[j] * e0 * e0;
+            xit[j] = x0[j];
+        }
+        __syncwarp();
+        const int irow = j < NX ? j : NX - 1;
+        for (int k = 0; k < N; ++k) {
+            const real* tile = Wv + (size_t)k * WT;
+            real wr[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) wr[c] = __ldg(tile + irow * 16 + h * 8 + c);
+            real u[4];
+            if (MODE != 2) {
+                const real* f = facv + (size_t)k * FAC;
+                Chol4<real> L;
+                L.load(f + 56);
+                const real xo = j < 3 ? xp[j] : (j < NX ? wv[j + 1] : real(0));
+                real v[4];
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) {
+                    real t = 0;
+                    if (j < NX) t = f[j * 4 + aa] * xo;
+                    else if (j == 13) t = f[(MODE == 0 ? 52 : 66) + aa];
+                    v[aa] = half_sum(hmask, t);
+                }
+                L.bsolve_neg(v, u);
+            } else {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) u[aa] = usol[k * 4 + aa];
+            }
+            __syncwarp();                       // everyone has read the old state
+            if (lane < 4) {
+                const real ul = lane == 0 ? u[0] : (lane == 1 ? u[1] : (lane == 2 ? u[2] : u[3]));
+                wv[lane] = ul;
+                if (MODE != 2) usol[k * 4 + lane] = ul;
+            }
+            __syncwarp();
+            real acc = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc += wr[c] * wv[h * 8 + c];
+            acc += __shfl_xor_sync(FULL, acc, 16);
+            if (j < 3) acc += xp[j];
+            __syncwarp();
+            if (h == 0 && j < NX) {
+                if (j < 3) xp[j] = acc; else wv[j + 1] = acc;
+                if (MODE == 2) {
+                    double* xo = xit + (size_t)(k + 1) * NX + j;
+                    const double xnew = *xo + double(acc);
+                    *xo = xnew;
+                    const real wgt = (k + 1 < N) ? a.Qd[j] : a.QNd[j];
+                    const double ref = (k + 1 < N) ? yref[(size_t)(k + 1) * NY + j] : yref_e[j];
+                    const real e = real(xnew - ref);
+                    cost += real(0.5) * wgt * e * e;
+                }
+            } else if (MODE == 2 && h == 1 && j < 4) {
+                const real e = real(double(ubar[k * 4 + j]) + double(u[j == 0 ? 0 : (j == 1 ? 1 : (j == 2 ? 2 : 3))]) - yref[(size_t)k * NY + NX + j]);
+                cost += real(0.5) * a.Rd[j] * e * e;
+            }
+            __syncwarp();
+        }
+        return cost;
+    }
+};
+
+template <typename real, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
+{
+    QMPC_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ocp = blockIdx.x * WARPS + warp;
+    if (ocp >= a.B) return;
+    const int N = a.N, E = 4 * N;
+    real* sm = reinterpret_cast<real*>(smem_raw) + (size_t)warp * a.smem_per_warp;
+    WarpCtx<real> c{a};
+    c.lane = lane; c.h = lane >> 4; c.j = lane & 15; c.ocp = ocp; c.N = N; c.E = E;
+    c.hmask = 0xffffu << (lane & 16);
+    c.sidx = (c.j < 3) ? c.j : ((c.j >= 4 && c.j < 14) ? c.j - 1 : -1);
+    c.P = sm + SM_P; c.pv = sm + SM_PV; c.wv = sm + SM_WV; c.xp = sm + SM_XP; c.hv = sm + SM_HV;
+    c.Ls = sm + SM_LS; c.cs = sm + SM_CS;
+    real* v = sm + SM_VEC;
+    c.rt = v; c.dR = v + E; c.usol = v + 2 * E; c.ua = v + 3 * E; c.ucur = v + 4 * E; c.ll = v + 5 * E;
+    c.lu = v + 6 * E; c.ubar = v + 7 * E; c.rdel = v + 8 * E; c.cl = v + 9 * E; c.cu = v + 10 * E;
+    c.Wv = a.W + (size_t)ocp * N * WT;
+    c.facv = a.fac + (size_t)ocp * N * FAC;
+    c.x0 = a.x0 + (size_t)ocp * NX;
+    c.yref = a.yref + (size_t)ocp * N * NY;
+    c.yref_e = a.yref_e + (size_t)ocp * NX;
+    c.xit = a.xit + (size_t)ocp * (N + 1) * NX;
+    c.uit = a.uit + (size_t)ocp * N * NU;
+
+    const real lb = a.lb, ub = a.ub;
+    for (int e = lane; e < E; e += 32) {
+        const real ub_ = real(c.uit[e]);
+        c.ubar[e] = ub_;
+        c.rdel[e] = a.Rd[e & 3] * (ub_ - real(c.yref[(size_t)(e >> 2) * NY + NX + (e & 3)]));
+        c.ucur[e] = real(0.5) * (lb + ub);
+        c.ll[e] = 1; c.lu[e] = 1;
+    }
+    __syncwarp();
+
+    int it = 0, status = QMPC_STATUS_MAXITER_;
+    const real inv2E = real(1) / real(2 * E);
+    while (true) {
+        real s = 0;
+        for (int e = lane; e < E; e += 32) s += c.ll[e] * (c.ucur[e] - lb) + c.lu[e] * (ub - c.ucur[e]);
+        const real mu = warp_sum(s) * inv2E;
+        if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
+        if (mu < a.mu_tol) { status = QMPC_STATUS_OK_; break; }
+        if (it >= a.max_iter) break;
+        // ---- predictor
+        for (int e = lane; e < E; e += 32) {
+            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
+            const real d = c.ll[e] / tl + c.lu[e] / tu;
+            c.dR[e] = d;
+            c.rt[e] = c.rdel[e] - d * (c.ucur[e] - c.ubar[e]);
+        }
+        __syncwarp();
+        c.backward_full();
+        c.template forward<0>();
+        __syncwarp();
+        real amin = 1;
+        for (int e = lane; e < E; e += 32) {
+            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
+            const real du = c.ubar[e] + c.usol[e] - c.ucur[e];
+            const real dl = -c.ll[e] - c.ll[e] / tl * du;
+            const real dv = -c.lu[e] + c.lu[e] / tu * du;
+            c.ua[e] = c.usol[e];
+            c.cl[e] = du * dl; c.cu[e] = -du * dv;
+            c.rt[e] = dl; c.dR[e] = dv;
+            if (du < 0) amin = fmin(amin, -tl / du);
+            if (du > 0) amin = fmin(amin, tu / du);
+            if (dl < 0) amin = fmin(amin, -c.ll[e] / dl);
+            if (dv < 0) amin = fmin(amin, -c.lu[e] / dv);
+        }
+        const real aaff = warp_min(amin);
+        s = 0;
+        for (int e = lane; e < E; e += 32) {
+            const real du = c.ubar[e] + c.ua[e] - c.ucur[e];
+            const real un = c.ucur[e] + aaff * du;
+            s += (c.ll[e] + aaff * c.rt[e]) * (un - lb) + (c.lu[e] + aaff * c.dR[e]) * (ub - un);
+        }
+        const real muaff = warp_sum(s) * inv2E;
+        real sigma = muaff / mu; sigma = sigma * sigma * sigma;
+        const real smu = sigma * mu;
+        // ---- corrector (increment on top of the predictor solution)
+        for (int e = lane; e < E; e += 32) {
+            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
+            c.rt[e] = -(smu - c.cl[e]) / tl + (smu - c.cu[e]) / tu;
+        }
+        __syncwarp();
+        c.backward_vec();
+        c.template forward<1>();
+        __syncwarp();
+        real amax = real(1e30);
+        for (int e = lane; e < E; e += 32) {
+            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
+            const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
+            const real dl = (smu - c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
+            const real dv = (smu - c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
+            c.usol[e] = du; c.rt[e] = dl; c.dR[e] = dv;
+            if (du < 0) amax = fmin(amax, -tl / du);
+            if (du > 0) amax = fmin(amax, tu / du);
+            if (dl < 0) amax = fmin(amax, -c.ll[e] / dl);
+            if (dv < 0) amax = fmin(amax, -c.lu[e] / dv);
+        }
+        const real alpha = fmin(real(1), real(0.995) * warp_min(amax));
+        for (int e = lane; e < E; e += 32) {
+            c.ucur[e] += alpha * c.usol[e];
+            c.ll[e] += alpha * c.rt[e];
+            c.lu[e] += alpha * c.dR[e];
+        }
+        ++it;
+    }
+    // ---- full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
+    for (int e = lane; e < E; e += 32) c.usol[e] = c.ucur[e] - c.ubar[e];
+    __syncwarp();
+    real cost = c.template forward<2>();
+    cost = warp_sum(cost);
+    for (int e = lane; e < E; e += 32) c.uit[e] = double(c.ucur[e]);
+    if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(c.ucur[lane]);
+    if (lane == 0) { a.cost[ocp] = double(cost); a.status[ocp] = status; a.iters[ocp] = it; }
+}
+
+}  // namespace qmpc

@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libqmpc.so) behind the reference's Python API,
+against the CPU oracle and the committed golden fixtures.  Tolerances (BASELINE.json north_star / SURVEY §8d):
+  fp64 solver: controls and predicted states within 1e-6 relative of the exact oracle, per step from identical
+               (x0, yref, alpha, iterate);  RGP mean/covariance within 1e-9 relative (always fp64);
+  distance to the acados logs is reported separately (<= 1e-5 abs on u0: HPIPM's own tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from conftest import rel_err
+from helpers import make_gp, oracle_solve_batch, random_ocp_batch, u_rel, x_rel
+
+pytestmark = pytest.mark.gpu
+
+TOL_U64 = 1e-6
+TOL_X64 = 1e-6
+TOL_RGP = 1e-9
+
+
+def _pkg():
+    from mpc_quad_ros_b200.quad import Quadrotor3D
+    from mpc_quad_ros_b200.quad_opt import quad_optimizer
+    from mpc_quad_ros_b200.gp.GPE import GPEnsemble
+    return Quadrotor3D, quad_optimizer, GPEnsemble
+
+
+def _solve_batch(sc, B, N, gp, precision=64, quad_name="hummingbird", mu_tol=0.0):
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    quad = Quadrotor3D(drag=True, batch=B)
+    quad = quad.set_hummingbird_params() if quad_name == "hummingbird" else quad.set_logged_pysim_params()
+    gpe = None
+    if gp is not None:
+        gpe = GPEnsemble.fromrange([(gp.X[d, 0], gp.X[d, -1]) for d in range(3)], [gp.M] * 3, theta=list(gp.theta[0]), batch=B)
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=precision, ipm_mu_tol=mu_tol)
+    opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
+    dev = opt.device
+    import ctypes as C
+    from mpc_quad_ros_b200 import _capi
+    yref = torch.as_tensor(sc["yref"], device=dev).contiguous()
+    yref_e = torch.as_tensor(sc["yref_e"], device=dev).contiguous()
+    _capi.check(_capi.lib().qmpc_set_yref(opt._h, _capi.ptr(yref), _capi.ptr(yref_e), _capi.stream_ptr()))
+    if gp is not None:
+        opt.set_rgp_params(torch.as_tensor(sc["mu"]))
+    x_opt, w_opt, t_cpu, cost = opt.run_optimization(torch.as_tensor(sc["x0"], device=dev))
+    st, it = opt.solver_status()
+    return x_opt.cpu().numpy(), w_opt.cpu().numpy(), cost.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
+
+
+@pytest.mark.parametrize("N,M", [(20, 20), (10, 0), (50, 20), (7, 50), (20, 100)])
+def test_solve_fp64_vs_oracle(N, M):
+    B, dt = 48, 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(M) if M else None
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=100 + N + M)
+    x, u, cost, st, it = _solve_batch(sc, B, N, gp)
+    xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
+    assert (st == 0).all(), st
+    assert u_rel(u, uo) < TOL_U64, u_rel(u, uo)
+    assert x_rel(x, xo) < TOL_X64, x_rel(x, xo)
+    assert np.abs(cost - co).max() < 1e-7 * max(1.0, np.abs(co).max())
+    assert ((u > 0 - 1e-12) & (u < 1 + 1e-12)).all()
+    assert np.abs(x[:, 0] - sc["x0"]).max() == 0.0
+    nact = ((uo < 1e-9) | (uo > 1 - 1e-9)).sum()
+    assert nact > 0                                    # the batch does exercise active thrust limits
+    print(f"N={N} M={M}: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} ipm iters mean={it.mean():.1f} (oracle {ito.mean():.1f})")
+
+
+def test_solve_full_baseline_batch_subset_vs_oracle():
+    """BASELINE config 2 size (4096 vehicles, N=20, M=20): every vehicle converges; a random subset of 64 is compared
+    with the oracle; the rest is covered by size-independent properties (bounds, x0 pin, determinism)."""
+    B, N, M = 4096, 20, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(M)
+    base = random_ocp_batch(128, N, dt, quad, gp, seed=7)
+    rep = B // 128
+    sc = {k: (None if v is None else np.concatenate([v] * rep)) for k, v in base.items()}
+    x, u, cost, st, it = _solve_batch(sc, B, N, gp)
+    assert (st == 0).all()
+    x2, u2, cost2, st2, it2 = _solve_batch(sc, B, N, gp)
+    assert np.array_equal(u, u2) and np.array_equal(x, x2)          # deterministic
+    assert np.array_equal(u[:128], u[128 * 5:128 * 6])               # replicated inputs -> identical outputs
+    assert ((u >= 0) & (u <= 1)).all()
+    idx = np.random.default_rng(0).choice(128, 64, replace=False)
+    xo, uo, co, ito = oracle_solve_batch(base, quad, dt, N, gp, idx)
+    assert u_rel(u[idx], uo) < TOL_U64 and x_rel(x[idx], xo) < TOL_X64
+
+
+@pytest.mark.parametrize("name,use_gp,nmax", [("traj2_v10_a10_gp0", False, None), ("traj0_v10_a10_gp2", True, None),
+                                              ("traj1_v15_a5_gp2", True, 46)])
+def test_golden_log_replay_through_reference_api(golden, name, use_gp, nmax):
+    """Replays the reference's shipped acados logs through quad_optimizer (single vehicle, numpy API)."""
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    g = golden(name)
+    N, dt = 10, 0.1
+    quad = Quadrotor3D(drag=True).set_logged_pysim_params()
+    gpe, gp = None, None
+    if use_gp:
+        X, th = g["rgp_X"], g["rgp_theta"]
+        gpe = GPEnsemble.fromrange([(X[d, 0], X[d, -1]) for d in range(3)], [X.shape[1]] * 3, theta=list(th[0]))
+        gp = orc.GPSpec(X, th)
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe)
+    xit, uit = np.zeros((N + 1, 13)), np.zeros((N, 4))
+    n = len(g["x_odom"]) if nmax is None else nmax
+    e_log, e_orc, e_cost = [], [], []
+    for i in range(min(n, len(g["x_ref"]) - N)):
+        x_ref = g["x_ref"][i:i + N]
+        yref, yref_N = opt.set_reference_trajectory(x_ref)
+        assert yref.shape == (N, 17) and np.all(yref[:, 13:] == 0.16) and np.array_equal(yref_N, x_ref[-1])
+        alpha = None
+        if use_gp:
+            p = np.zeros((3, gp.M)) if i == 0 else g["rgp_mu"][i - 1]
+            opt.set_rgp_params(p)
+            alpha = gp.alpha(p)
+        x_opt, w_opt, t_cpu, cost = opt.run_optimization(g["x_odom"][i])
+        yr, yre = orc.make_yref(x_ref)
+        orc.rti_step(orc.quad_logged_pysim(), dt, N, g["x_odom"][i], yr, yre, xit, uit, gp=gp, alpha=alpha)
+        e_log.append(np.abs(w_opt[0] - g["w_odom"][i]).max())
+        e_orc.append(max(np.abs(w_opt - uit).max(), np.abs(x_opt - xit).max() / max(1.0, np.abs(xit).max())))
+        e_cost.append(abs(cost - g["cost_solution"][i]) / abs(g["cost_solution"][i]))
+        # keep both iterates identical so that every step is a per-step parity check (SURVEY §8c caveat)
+        opt.set_iterate(xit[None], uit[None])
+    e_log, e_orc = np.array(e_log), np.array(e_orc)
+    print(f"{name}: vs acados log median {np.median(e_log):.1e} max {e_log.max():.1e}; vs oracle max {e_orc.max():.1e}; cost rel {max(e_cost):.1e}")
+    assert e_orc.max() < TOL_U64
+    assert np.median(e_log) < 5e-8 and e_log.max() < 1e-5
+    assert max(e_cost) < 2e-5
+
+
+def test_golden_log_free_running_replay(golden):
+    """Same log, but the GPU solver carries its OWN iterate across all 289 steps (no injection): contractive log."""
+    Quadrotor3D, quad_optimizer, _ = _pkg()
+    g = golden("traj2_v10_a10_gp0")
+    N = 10
+    opt = quad_optimizer(Quadrotor3D(drag=True).set_logged_pysim_params(), t_horizon=1.0, n_nodes=N)
+    errs = []
+    for i in range(len(g["x_ref"]) - N):
+        opt.set_reference_trajectory(g["x_ref"][i:i + N])
+        x_opt, w_opt, _, cost = opt.run_optimization(g["x_odom"][i])
+        errs.append(np.abs(w_opt[0] - g["w_odom"][i]).max())
+    assert np.median(errs) < 5e-8 and max(errs) < 1e-5
+
+
+@pytest.mark.parametrize("name,tol", [("traj0_v10_a10_gp2", TOL_RGP), ("traj1_v15_a5_gp2", TOL_RGP), ("traj0_v15_a5_gp2", TOL_RGP),
+                                      ("traj2_v10_a10_gp2", 1e-7)])
+def test_rgp_regress_golden_logs(golden, name, tol):
+    """GPEnsemble.regress against the logged RGP state sequences (list-in / list-out reference API);
+    the last log is the reference's own DIVERGING run (mu -> 1e12), kept as an operand-order stress."""
+    _, _, GPEnsemble = _pkg()
+    g = golden(name)
+    X, th = g["rgp_X"], g["rgp_theta"]
+    gpe = GPEnsemble.fromrange([(X[d, 0], X[d, -1]) for d in range(3)], [X.shape[1]] * 3, theta=list(th[0]))
+    assert gpe.type == "RGP" and np.allclose(gpe.gp[0].X, X[0])
+    worst_mu = worst_C = 0.0
+    for i in range(len(g["v_body"])):
+        mu, Cm = gpe.regress([np.array([g["v_body"][i, d]]) for d in range(3)], [np.array([g["a_drag"][i, d]]) for d in range(3)])
+        worst_mu = max(worst_mu, rel_err(np.stack(mu), g["rgp_mu"][i]))
+        worst_C = max(worst_C, rel_err(np.stack(Cm), g["rgp_C"][i]))
+    print(f"{name}: rgp rel err mu {worst_mu:.1e} C {worst_C:.1e}")
+    assert worst_mu < tol and worst_C < tol
+    assert np.array_equal(gpe.gp[1].mu_g_t, mu[1]) and gpe.gp[2].C_g_t.shape == (X.shape[1],) * 2
+
+
+@pytest.mark.parametrize("tag", ["m20", "m50", "m7"])
+def test_rgp_reference_code_fixture_batched(golden, tag):
+    """RGP.regress / predict / predict_using_y outputs of the reference's own numpy code (M = 20, 50, 7), with the
+    vehicles of a batch fed the same sequence at different offsets (ragged progress)."""
+    _, _, GPEnsemble = _pkg()
+    g = golden("reference_code")
+    X, th = g[f"rgp_{tag}_X"], g[f"rgp_{tag}_theta"]
+    M, T = X.shape[1], len(g[f"rgp_{tag}_xt"])
+    B = 5
+    gpe = GPEnsemble.fromrange([(X[d, 0], X[d, -1]) for d in range(3)], [M] * 3, theta=list(th[0]), batch=B)
+    assert rel_err(gpe.K_x_inv, g[f"rgp_{tag}_Kx_inv"]) < 1e-9
+    xt, yt = g[f"rgp_{tag}_xt"], g[f"rgp_{tag}_yt"]
+    for t in range(T):
+        # vehicle b is b samples behind; NaN = "no sample for this vehicle yet" (axis skipped by the kernel)
+        xb = np.stack([xt[t - b] if t - b >= 0 else np.full(3, np.nan) for b in range(B)])
+        yb = np.stack([yt[t - b] if t - b >= 0 else np.zeros(3) for b in range(B)])
+        mu, Cm = gpe.regress(torch.as_tensor(xb), torch.as_tensor(yb))
+    mu, Cm = mu.cpu().numpy(), Cm.cpu().numpy()
+    for b in range(B):
+        assert rel_err(mu[b], g[f"rgp_{tag}_mu"][T - 1 - b]) < TOL_RGP
+        assert rel_err(Cm[b], g[f"rgp_{tag}_C"][T - 1 - b]) < TOL_RGP
+    xs = g[f"rgp_{tag}_pred_x"]
+    mean, std = gpe.predict(torch.as_tensor(np.broadcast_to(xs, (B, 3, len(xs))).copy()), std=True)
+    assert rel_err(mean[0].cpu().numpy(), g[f"rgp_{tag}_pred_mean"]) < TOL_RGP
+    var_ref = g[f"rgp_{tag}_pred_var"]
+    assert np.abs(std[0].cpu().numpy() ** 2 - var_ref).max() < 1e-9 * max(1.0, np.abs(var_ref).max())
+    y = g[f"rgp_{tag}_puy_y"]
+    puy = gpe.predict_using_y(torch.as_tensor(np.broadcast_to(xs, (B, 3, len(xs))).copy()), torch.as_tensor(np.broadcast_to(y, (B, 3, M)).copy()))
+    assert rel_err(puy[0].cpu().numpy(), g[f"rgp_{tag}_puy_mean"]) < TOL_RGP
+    # alpha = K_x^-1 mu is what the OCP model consumes
+    al = gpe.alpha_tensor().cpu().numpy()
+    assert rel_err(al[0], np.einsum("dij,dj->di", g[f"rgp_{tag}_Kx_inv"], mu[0])) < 1e-9
+
+
+def test_helpers_vs_golden(golden):
+    from mpc_quad_ros_b200.utils import utils
+    Quadrotor3D, quad_optimizer, _ = _pkg()
+    g, gl = golden("reference_code"), golden("traj0_v10_a10_gp2")
+    # compute_a_drag: reference list format for one vehicle, tensors for a batch
+    vb, ad = utils.compute_a_drag(g["drag_x_now"][0], g["drag_x_pred"][0], float(g["drag_dt"]))
+    assert isinstance(vb, list) and len(vb) == 3 and vb[0].shape == (1,)
+    vbt, adt = utils.compute_a_drag(torch.as_tensor(g["drag_x_now"]).cuda(), torch.as_tensor(g["drag_x_pred"]).cuda(), float(g["drag_dt"]))
+    assert np.abs(vbt.cpu().numpy() - g["drag_v_body"]).max() < 1e-13
+    assert np.abs(adt.cpu().numpy() - g["drag_a_drag"]).max() < 1e-11
+    assert abs(vb[1][0] - g["drag_v_body"][0, 1]) < 1e-13
+    # get_reference_chunk incl. end padding and skip: bit exact
+    for n, (idx, N, skip) in enumerate(g["chunk_cases"]):
+        out = utils.get_reference_chunk(g["chunk_traj"], int(idx), int(N), int(skip))
+        assert np.array_equal(out, g[f"chunk_{n}"]), (idx, N, skip)
+    # discrete_dynamics (nominal RK4) against the logged one-step predictions
+    quad = Quadrotor3D(drag=True).set_logged_pysim_params()
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=10)
+    xp = opt.discrete_dynamics(torch.as_tensor(gl["x_odom"]).cuda(), torch.as_tensor(gl["w_odom"]).cuda(), 0.1)
+    assert np.abs(xp.cpu().numpy() - gl["x_pred_odom"]).max() < 1e-13
+    x1 = opt.discrete_dynamics(gl["x_odom"][3], gl["w_odom"][3], 0.1)
+    assert x1.shape == (13,) and np.abs(x1 - gl["x_pred_odom"][3]).max() < 1e-13
+    xb = opt.discrete_dynamics(gl["x_odom"][3], gl["w_odom"][3], 0.1, body_frame=True)
+    assert np.abs(xb[7:10] - orc.compute_a_drag(x1, x1, 0.1)[0]).max() < 1e-13
+    with pytest.raises(AssertionError):
+        opt.discrete_dynamics(np.zeros(12), np.zeros(4), 0.1)
+    with pytest.raises(ValueError):
+        opt.run_optimization(None)
+    # plant (Quadrotor3D.update over one control period) against the reference's own class
+    for tag in ("hb", "log"):
+        xs, us, xn = g[f"plant_{tag}_x"], g[f"plant_{tag}_u"], g[f"plant_{tag}_xnext"]
+        q = Quadrotor3D(drag=True, batch=len(xs))
+        q = q.set_hummingbird_params() if tag == "hb" else q.set_logged_pysim_params()
+        q.set_state(xs)
+        for _ in range(11):
+            q.update(torch.as_tensor(us), 5e-3)
+        assert np.abs(q.get_state(quaternion=True, stacked=True).cpu().numpy() - xn).max() < 1e-12
+
+
+@pytest.mark.parametrize("use_gp", [True, False])
+def test_closed_loop_vs_oracle(use_gp):
+    """ClosedLoop (fused qmpc_step + plant + chunk on the GPU) against the oracle's closed loop, 32 vehicles x 12 steps,
+    BASELINE shape N=20, M=20.  Both loops run freely (no injection): over 12 steps they stay within tolerance."""
+    from mpc_quad_ros_b200.execute_trajectory import ClosedLoop
+    from mpc_quad_ros_b200.trajectory import random_smooth_trajectories
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    B, N, M, steps = 32, 20, 20, 12
+    dt = 1.0 / N
+    quad = Quadrotor3D(drag=True, batch=B).set_hummingbird_params()
+    gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B) if use_gp else None
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe)
+    traj = random_smooth_trajectories(B, steps + N + 3, dt)
+    x0 = traj[:, 0, :].copy()
+    x0[:, :3] += np.random.default_rng(3).uniform(-0.5, 0.5, (B, 3))
+    loop = ClosedLoop(quad, opt, torch.as_tensor(traj), torch.as_tensor(x0))
+    assert loop.n_sub == 11
+    xs, us = loop.run(steps, record=True)
+    ref = orc.ClosedLoop(orc.quad_hummingbird(), dt, N, traj, x0, gp=make_gp(M) if use_gp else None)
+    r = ref.run(steps)
+    assert r["bad"] == 0
+    assert u_rel(us.cpu().numpy(), r["u0"]) < TOL_U64
+    assert x_rel(xs.cpu().numpy(), r["x"]) < TOL_X64
+    if use_gp:
+        assert rel_err(gpe.mu_tensor().cpu().numpy(), ref.mu) < 1e-7      # closed-loop accumulation of 1e-9-level terms
+        assert rel_err(gpe.C_tensor().cpu().numpy(), ref.C) < TOL_RGP
+
+
+def test_simulate_trajectory_single_vehicle_reference_api():
+    """The reference's loop, method by method, for ONE vehicle with numpy in/out (drop-in surface), RGP in the loop."""
+    from mpc_quad_ros_b200.execute_trajectory import simulate_trajectory
+    from mpc_quad_ros_b200.trajectory import sample_circle_trajectory_accelerating
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    N, steps = 10, 15
+    quad = Quadrotor3D(payload=False, drag=True).set_logged_pysim_params()
+    x0 = np.array([0.0, 0.0, 3.0] + [1.0, 0.0, 0.0, 0.0] + [0.0] * 6)
+    quad.set_state(x0)
+    gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [10] * 3, theta=[3.0, 0.1, 0.01])
+    opt = quad_optimizer(quad, t_horizon=1, n_nodes=N, gpe=gpe)
+    nominal = quad_optimizer(quad, t_horizon=1, n_nodes=N, gpe=None)
+    traj, t = sample_circle_trajectory_accelerating(10, 10, 30, opt.optimization_dt)
+    log = simulate_trajectory(quad, opt, nominal, x0, traj, max(t), steps, 5e-3)
+    assert isinstance(log["w_odom"][0], np.ndarray) and log["w_odom"][0].shape == (4,)
+    assert isinstance(log["rgp_mu_g_t"][0], list) and log["rgp_mu_g_t"][0][0].shape == (10,)
+    ref = orc.ClosedLoop(orc.quad_logged_pysim(), 0.1, N, traj[None], x0[None], gp=make_gp(10))
+    r = ref.run(steps)
+    u = np.array(log["w_odom"])
+    assert u_rel(u, r["u0"][:, 0]) < TOL_U64
+    assert rel_err(np.stack(log["rgp_mu_g_t"][-1]), ref.mu[0]) < 1e-7
+
+
+def test_fp32_solver_runs_and_is_close():
+    """fp32 Riccati/IPM build: finite, feasible, and close to the oracle on non-degenerate problems.  The 1e-4 bar of
+    north_star needs the active-set polish that is not in the fp32 path yet (DESIGN.md, fp32 status) -> reported, loose."""
+    B, N, M = 48, 20, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(M)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=11, amp_choices=(2.0,))
+    x, u, cost, st, it = _solve_batch(sc, B, N, gp, precision=32)
+    xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
+    assert np.isfinite(u).all() and ((u >= 0) & (u <= 1)).all()
+    print(f"fp32: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} status={np.bincount(st)}")
+    assert u_rel(u, uo) < 5e-2
