@@ -34,7 +34,7 @@ extern "C" {
 #define QMPC_ERR_ALLOC (-3)
 
 /* per-vehicle solver status written by qmpc_solve */
-#define QMPC_STATUS_OK 0        /* IPM converged (complementarity below ipm_mu_tol)          */
+#define QMPC_STATUS_OK 0        /* exact active set verified, or IPM converged below ipm_mu_tol */
 #define QMPC_STATUS_MAXITER 1   /* ipm_max_iter reached (reference: qp_solver_iter_max = 50)  */
 #define QMPC_STATUS_NAN 2       /* NaN/Inf met                                                */
 
@@ -50,7 +50,10 @@ typedef struct {
     int precision;       /* 64: fp64 solver (default) ; 32: fp32 Riccati/IPM (RGP stays fp64)        */
     int device;          /* CUDA device ordinal                                                       */
     int ipm_max_iter;    /* <=0 -> 50                                                                  */
-    double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32)                                          */
+    int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 10, <0 -> off (pure IPM)     */
+    int reserved_;
+    double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32): complementarity target of the pure IPM     */
+    double ipm_mu_switch; /* <=0 -> 1e-6 (fp64) / 1e-4 (fp32): IPM hands over to the refinement below this */
     double t_horizon;    /* tf ; dt = t_horizon / n_nodes (quad_opt.py:43)                            */
     double quad[20];     /* mass, max_thrust, J[3], x_f[4], y_f[4], z_l_tau[4], g[3]                  */
     double w_diag[17];   /* LINEAR_LS stage weights diag(W) (quad_opt.py:122-129); scaled by dt inside */

@@ -122,7 +122,10 @@ struct IpmArgs {
     int B, N;
     real Qd[13], QNd[13], Rd[4];   // dt*W_x, W_e, dt*W_u
     real dt, lb, ub, mu_tol;
+    real mu_switch;                // complementarity at which the IPM hands over to the active-set refinement
+    real refine_gtol;              // sign tolerance on the multipliers of pinned inputs
     int max_iter;
+    int max_refine;                // 0 = pure IPM down to mu_tol
     int smem_per_warp;             // reals
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
@@ -188,8 +191,8 @@ constexpr int SM_XP = 232;     // 16  position part of the forward state
 constexpr int SM_HV = 248;     // 16  h = P b + p
 constexpr int SM_LS = 264;     // 64  l_j per tile column
 constexpr int SM_CS = 328;     // 32  Muu(16) Mpu(12) gu(4)
-constexpr int SM_VEC = 360;    // 11 vectors of 4N
-constexpr int SM_NVEC = 11;
+constexpr int SM_VEC = 360;    // 13 vectors of 4N, then the state trajectory (N+1) x 13 of the refinement
+constexpr int SM_NVEC = 13;
 
 template <typename real>
 struct WarpCtx {
@@ -197,7 +200,8 @@ struct WarpCtx {
     int lane, h, j, sidx, ocp, N, E;
     unsigned hmask;
     real *P, *pv, *wv, *xp, *hv, *Ls, *cs;
-    real *rt, *dR, *usol, *ua, *ucur, *ll, *lu, *ubar, *rdel, *cl, *cu;
+    real *rt, *dR, *usol, *ua, *ucur, *ll, *lu, *ubar, *rdel, *cl, *cu, *tl, *tu, *xtr;
+    real *fx, *fv, *grad;          // aliases of cl, cu, ua while the active set is refined
     const real* Wv;
     real* facv;
     const double *x0, *yref, *yref_e;
@@ -211,6 +215,9 @@ struct WarpCtx {
     }
 
     // backward Riccati sweep with factorisation; gradient: rt (inputs), q column (states), b column (offset)
+    // FIXED: inputs flagged in fx are pinned at fv (exact elimination: their rows/columns of M_uu, M_ux become
+    // identity/zero and M[:,a] fv_a moves into the gradient).
+    template <bool FIXED>
     __device__ void backward_full()
     {
         for (int idx = lane; idx < 196; idx += 32) P[idx] = 0;
@@ -264,16 +271,32 @@ struct WarpCtx {
 #pragma unroll
             for (int c = 0; c < NX; ++c) g += w[c] * hv[c];
             g += (j < 4) ? rt[k * 4 + j] : qj;
-            if (lane < 4) {
+            real mu4[4];                         // rows 0..3 (inputs) of this lane's column; they live in the h=0 half
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) cs[aa * 4 + lane] = m[aa];
+            for (int aa = 0; aa < 4; ++aa) mu4[aa] = __shfl_sync(FULL, m[aa], j);
+            real fxa[4] = {0, 0, 0, 0}, fva[4] = {0, 0, 0, 0};
+            if (FIXED) {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) { fxa[aa] = fx[k * 4 + aa]; fva[aa] = fv[k * 4 + aa]; }
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) g += mu4[aa] * fva[aa];   // M[:,a] fv_a -> gradient
+            }
+            if (lane < 4) {
+                const bool mefix = FIXED && (lane == 0 ? fxa[0] : (lane == 1 ? fxa[1] : (lane == 2 ? fxa[2] : fxa[3]))) != real(0);
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) {
+                    real v = m[aa];
+                    if (FIXED && (mefix || fxa[aa] != real(0))) v = (aa == lane) ? real(1) : real(0);
+                    cs[aa * 4 + lane] = v;
+                }
 #pragma unroll
                 for (int pi = 0; pi < 3; ++pi) cs[16 + pi * 4 + lane] = yf[pi];
-                cs[28 + lane] = g;
+                cs[28 + lane] = mefix ? real(0) : g;
             }
             __syncwarp();
             Chol4<real> L;
-            real lg[4], lp[3][4], lj[4], mu4[4];
+            real lg[4], lp[3][4], lj[4];
+            real gpc[3] = {0, 0, 0};             // gradient correction of the position rows from pinned inputs
             {
                 real Muu[16];
 #pragma unroll
@@ -281,10 +304,20 @@ struct WarpCtx {
                 L.factor(Muu);
                 L.fsolve(cs + 28, lg);
 #pragma unroll
-                for (int pi = 0; pi < 3; ++pi) L.fsolve(cs + 16 + pi * 4, lp[pi]);
-            }
+                for (int pi = 0; pi < 3; ++pi) {
+                    real mpu[4];
 #pragma unroll
-            for (int aa = 0; aa < 4; ++aa) mu4[aa] = __shfl_sync(FULL, m[aa], j);   // rows 0..3 live in the h=0 half
+                    for (int aa = 0; aa < 4; ++aa) {
+                        mpu[aa] = cs[16 + pi * 4 + aa];
+                        if (FIXED && fxa[aa] != real(0)) { gpc[pi] += mpu[aa] * fva[aa]; mpu[aa] = 0; }
+                    }
+                    L.fsolve(mpu, lp[pi]);
+                }
+            }
+            if (FIXED) {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) mu4[aa] = 0;
+            }
             L.fsolve(mu4, lj);
             real lpme[4];                       // l_p of "my" position state (lanes 0..2)
 #pragma unroll
@@ -316,7 +349,7 @@ struct WarpCtx {
 #pragma unroll
                     for (int pi = 0; pi < 3; ++pi)
                         P[pi * 14 + lane] += ((pi == lane) ? a.Qd[lane] : real(0)) - dot4(lp[pi], lpme);
-                    pv[lane] = hv[lane] + qj - dot4(lpme, lg);
+                    pv[lane] = hv[lane] + qj + (lane == 0 ? gpc[0] : (lane == 1 ? gpc[1] : gpc[2])) - dot4(lpme, lg);
                 }
             }
             if (h == 0) {
@@ -381,15 +414,76 @@ struct WarpCtx {
         }
     }
 
+    // adjoint sweep at the point (xtr, usol): grad[e] = d(objective)/d(u_e) through the linearised dynamics
+    __device__ void backward_adjoint()
+    {
+        if (lane < NX) pv[lane] = a.QNd[lane] * (xtr[(size_t)N * NX + lane] + real(xit[(size_t)N * NX + lane] - yref_e[lane]));
+        __syncwarp();
+        real w[NX], wn[NX];
+        load_col(N - 1, w);
+        for (int k = N - 1; k >= 0; --k) {
+            if (k > 0) load_col(k - 1, wn);
+            const real* tile = Wv + (size_t)k * WT;
+            const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
+            real g = 0;
+#pragma unroll
+            for (int c = 0; c < NX; ++c) g += w[c] * pv[c];
+            const real xk = sidx >= 0 ? xtr[k * NX + sidx] : real(0);
+            const real pold = j < 3 ? pv[j] : real(0);
+            __syncwarp();
+            if (h == 0) {
+                if (j < 4) grad[k * 4 + j] = g + a.Rd[j] * usol[k * 4 + j] + rdel[k * 4 + j];
+                if (j >= 4 && j < 14) pv[j - 1] = g + a.Qd[j - 1] * xk + qj;
+                else if (j < 3) pv[j] = pold + a.Qd[j] * xk + qj;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NX; ++i) w[i] = wn[i];
+        }
+    }
+
+    // Primal-dual active-set refinement from the IPM's guess of the active set.  Each round solves the LQR with the
+    // active inputs pinned (one factorisation + one forward sweep) and checks the multipliers with an adjoint sweep.
+    // Returns true when the active set is self-consistent: usol then holds the exact minimiser of the box-QP.
+    __device__ bool refine_active_set(real lb, real ub)
+    {
+        for (int e = lane; e < E; e += 32) {
+            fx[e] = tl[e] < ll[e] ? real(1) : (tu[e] < lu[e] ? real(2) : real(0));
+            dR[e] = 0; rt[e] = rdel[e];
+        }
+        for (int round = 0; round < a.max_refine; ++round) {
+            for (int e = lane; e < E; e += 32) fv[e] = fx[e] == real(1) ? lb - ubar[e] : (fx[e] == real(2) ? ub - ubar[e] : real(0));
+            __syncwarp();
+            backward_full<true>();
+            forward<0, true>();
+            __syncwarp();
+            backward_adjoint();
+            __syncwarp();
+            int changed = 0;
+            for (int e = lane; e < E; e += 32) {
+                const real f = fx[e], un = ubar[e] + usol[e], gr = grad[e];
+                if (f == real(1)) { if (gr < -a.refine_gtol) { fx[e] = 0; changed = 1; } }
+                else if (f == real(2)) { if (gr > a.refine_gtol) { fx[e] = 0; changed = 1; } }
+                else if (un < lb) { fx[e] = 1; changed = 1; }
+                else if (un > ub) { fx[e] = 2; changed = 1; }
+            }
+            changed = warp_max(changed);
+            if (!changed) return true;
+        }
+        return false;
+    }
+
     // forward sweep.  MODE 0: feedback with lg and offset b (predictor, writes usol)
     //                 MODE 1: feedback with lgc, homogeneous (corrector increment, writes usol)
     //                 MODE 2: open loop with usol, offset b; writes the new iterate and returns the objective
-    template <int MODE>
+    //                 FIXED (with MODE 0): pinned inputs take fv; the state trajectory is kept in xtr for the adjoint
+    template <int MODE, bool FIXED = false>
     __device__ real forward()
     {
         if (lane < NX) {
             const real v = MODE == 1 ? real(0) : real(x0[lane] - xit[lane]);
             if (lane < 3) xp[lane] = v; else wv[lane + 1] = v;
+            if (FIXED) xtr[lane] = v;
         } else if (lane == 14) wv[14] = MODE == 1 ? real(0) : real(1);
         else if (lane == 15) wv[15] = 0;
         real cost = 0;
@@ -420,6 +514,10 @@ struct WarpCtx {
                     v[aa] = half_sum(hmask, t);
                 }
                 L.bsolve_neg(v, u);
+                if (FIXED) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) if (fx[k * 4 + aa] != real(0)) u[aa] = fv[k * 4 + aa];
+                }
             } else {
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) u[aa] = usol[k * 4 + aa];
@@ -439,6 +537,7 @@ struct WarpCtx {
             __syncwarp();
             if (h == 0 && j < NX) {
                 if (j < 3) xp[j] = acc; else wv[j + 1] = acc;
+                if (FIXED) xtr[(k + 1) * NX + j] = acc;
                 if (MODE == 2) {
                     double* xo = xit + (size_t)(k + 1) * NX + j;
                     const double xnew = *xo + double(acc);
@@ -476,6 +575,8 @@ __global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
     real* v = sm + SM_VEC;
     c.rt = v; c.dR = v + E; c.usol = v + 2 * E; c.ua = v + 3 * E; c.ucur = v + 4 * E; c.ll = v + 5 * E;
     c.lu = v + 6 * E; c.ubar = v + 7 * E; c.rdel = v + 8 * E; c.cl = v + 9 * E; c.cu = v + 10 * E;
+    c.tl = v + 11 * E; c.tu = v + 12 * E; c.xtr = v + 13 * E;
+    c.fx = c.cl; c.fv = c.cu; c.grad = c.ua;
     c.Wv = a.W + (size_t)ocp * N * WT;
     c.facv = a.fac + (size_t)ocp * N * FAC;
     c.x0 = a.x0 + (size_t)ocp * NX;
@@ -489,34 +590,43 @@ __global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
         const real ub_ = real(c.uit[e]);
         c.ubar[e] = ub_;
         c.rdel[e] = a.Rd[e & 3] * (ub_ - real(c.yref[(size_t)(e >> 2) * NY + NX + (e & 3)]));
-        c.ucur[e] = real(0.5) * (lb + ub);
+        const real u0 = real(0.5) * (lb + ub);
+        c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0;     // slacks are carried, never recomputed from u
         c.ll[e] = 1; c.lu[e] = 1;
     }
     __syncwarp();
 
     int it = 0, status = QMPC_STATUS_MAXITER_;
+    bool exact = false;
+    bool refine = a.max_refine > 0;
+    real target = refine ? a.mu_switch : a.mu_tol;
     const real inv2E = real(1) / real(2 * E);
     while (true) {
         real s = 0;
-        for (int e = lane; e < E; e += 32) s += c.ll[e] * (c.ucur[e] - lb) + c.lu[e] * (ub - c.ucur[e]);
+        for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
         const real mu = warp_sum(s) * inv2E;
         if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
-        if (mu < a.mu_tol) { status = QMPC_STATUS_OK_; break; }
+        if (mu < target) {
+            if (refine) {
+                if (c.refine_active_set(lb, ub)) { status = QMPC_STATUS_OK_; exact = true; break; }
+                refine = false; target = a.mu_tol;           // inconsistent active set: resume the IPM to the tight tolerance
+                if (mu < target) { status = QMPC_STATUS_OK_; break; }
+            } else { status = QMPC_STATUS_OK_; break; }
+        }
         if (it >= a.max_iter) break;
         // ---- predictor
         for (int e = lane; e < E; e += 32) {
-            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
-            const real d = c.ll[e] / tl + c.lu[e] / tu;
+            const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];
             c.dR[e] = d;
             c.rt[e] = c.rdel[e] - d * (c.ucur[e] - c.ubar[e]);
         }
         __syncwarp();
-        c.backward_full();
+        c.template backward_full<false>();
         c.template forward<0>();
         __syncwarp();
         real amin = 1;
         for (int e = lane; e < E; e += 32) {
-            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
+            const real tl = c.tl[e], tu = c.tu[e];
             const real du = c.ubar[e] + c.usol[e] - c.ucur[e];
             const real dl = -c.ll[e] - c.ll[e] / tl * du;
             const real dv = -c.lu[e] + c.lu[e] / tu * du;
@@ -532,24 +642,21 @@ __global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
         s = 0;
         for (int e = lane; e < E; e += 32) {
             const real du = c.ubar[e] + c.ua[e] - c.ucur[e];
-            const real un = c.ucur[e] + aaff * du;
-            s += (c.ll[e] + aaff * c.rt[e]) * (un - lb) + (c.lu[e] + aaff * c.dR[e]) * (ub - un);
+            s += (c.ll[e] + aaff * c.rt[e]) * (c.tl[e] + aaff * du) + (c.lu[e] + aaff * c.dR[e]) * (c.tu[e] - aaff * du);
         }
         const real muaff = warp_sum(s) * inv2E;
         real sigma = muaff / mu; sigma = sigma * sigma * sigma;
         const real smu = sigma * mu;
         // ---- corrector (increment on top of the predictor solution)
-        for (int e = lane; e < E; e += 32) {
-            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
-            c.rt[e] = -(smu - c.cl[e]) / tl + (smu - c.cu[e]) / tu;
-        }
+        for (int e = lane; e < E; e += 32)
+            c.rt[e] = -(smu - c.cl[e]) / c.tl[e] + (smu - c.cu[e]) / c.tu[e];
         __syncwarp();
         c.backward_vec();
         c.template forward<1>();
         __syncwarp();
         real amax = real(1e30);
         for (int e = lane; e < E; e += 32) {
-            const real tl = c.ucur[e] - lb, tu = ub - c.ucur[e];
+            const real tl = c.tl[e], tu = c.tu[e];
             const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
             const real dl = (smu - c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
             const real dv = (smu - c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
@@ -561,13 +668,20 @@ __global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
         }
         const real alpha = fmin(real(1), real(0.995) * warp_min(amax));
         for (int e = lane; e < E; e += 32) {
-            c.ucur[e] += alpha * c.usol[e];
+            const real du = alpha * c.usol[e];
+            c.ucur[e] += du; c.tl[e] += du; c.tu[e] -= du;
             c.ll[e] += alpha * c.rt[e];
             c.lu[e] += alpha * c.dR[e];
         }
         ++it;
     }
     // ---- full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
+    for (int e = lane; e < E; e += 32) {
+        real un;
+        if (exact) un = c.fx[e] == real(1) ? lb : (c.fx[e] == real(2) ? ub : c.ubar[e] + c.usol[e]);
+        else un = fmin(fmax(c.ucur[e], lb), ub);
+        c.ucur[e] = un;
+    }
     for (int e = lane; e < E; e += 32) c.usol[e] = c.ucur[e] - c.ubar[e];
     __syncwarp();
     real cost = c.template forward<2>();

@@ -21,7 +21,7 @@ R_COST = np.array([0.1, 0.1, 0.1, 0.1])
 
 class quad_optimizer:
     def __init__(self, quad, t_horizon=1, n_nodes=100, gpe=None, batch=None, device=None, precision=64,
-                 ipm_mu_tol=0.0, ipm_max_iter=50):
+                 ipm_mu_tol=0.0, ipm_max_iter=50, ipm_mu_switch=0.0, refine_max_rounds=0):
         self.n_nodes, self.t_horizon, self.gpe = n_nodes, t_horizon, gpe
         self.optimization_dt = self.t_horizon / self.n_nodes
         self.terminal_cost = 1
@@ -42,6 +42,7 @@ class quad_optimizer:
         cfg.batch, cfg.n_nodes, cfg.n_basis = self.batch, n_nodes, (0 if gpe is None else gpe.M)
         cfg.precision, cfg.device = precision, (self.device.index or 0)
         cfg.ipm_max_iter, cfg.ipm_mu_tol, cfg.t_horizon = ipm_max_iter, ipm_mu_tol, float(t_horizon)
+        cfg.ipm_mu_switch, cfg.refine_max_rounds = ipm_mu_switch, refine_max_rounds   # 0 -> library defaults
         cfg.quad[:] = list(quad.quad_vector())
         cfg.w_diag[:] = list(np.diag(self.W))
         cfg.we_diag[:] = list(np.diag(self.W_e))

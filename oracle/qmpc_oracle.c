@@ -389,80 +389,83 @@ static void qp_gradient(const qp_t *qp, const double *us, double *xs, double *gu
     }
 }
 
-/* Mehrotra predictor-corrector on the box-QP, then exact active-set polish.
-   returns status: 0 exact (polished), 1 IPM converged but polish rejected, 2 max iterations, 3 NaN */
+int orc_last_rounds = 0;   /* refinement rounds of the most recent boxqp_solve (diagnostic, not thread safe) */
+
+/* Mehrotra predictor-corrector on the box-QP, then exact active-set refinement.
+   The slacks t_l = u - lb, t_u = ub - u are carried as independent positive variables (updated with the step, never
+   recomputed from u) so that complementarity can be driven far below the spacing of doubles around the bounds.
+   returns status: 0 exact (active set verified), 1 IPM converged but refinement rejected, 2 max iterations, 3 NaN */
 static int boxqp_solve(const qp_t *qp, double *xs, double *us, int *iters_out, double *kkt_out,
                        double mu_tol, int max_iter, int do_polish)
 {
     int N = qp->N, n = N * NU;
-    double *u = (double *)malloc(sizeof(double) * n), *ll = (double *)malloc(sizeof(double) * n);
-    double *lu = (double *)malloc(sizeof(double) * n), *dR = (double *)malloc(sizeof(double) * n);
-    double *rt = (double *)malloc(sizeof(double) * n), *ua = (double *)malloc(sizeof(double) * n);
-    double *uc = (double *)malloc(sizeof(double) * n), *xw = (double *)malloc(sizeof(double) * (N + 1) * NX);
-    double *dla = (double *)malloc(sizeof(double) * n), *dua = (double *)malloc(sizeof(double) * n);
+    double *buf = (double *)malloc(sizeof(double) * (11 * n + (N + 1) * NX));
+    double *u = buf, *ll = buf + n, *lu = buf + 2 * n, *dR = buf + 3 * n, *rt = buf + 4 * n, *ua = buf + 5 * n;
+    double *uc = buf + 6 * n, *dla = buf + 7 * n, *dua = buf + 8 * n, *tl = buf + 9 * n, *tu = buf + 10 * n;
+    double *xw = buf + 11 * n;
     double lb = qp->lb, ub = qp->ub;
-    for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); ll[i] = 1.0; lu[i] = 1.0; }
+    for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); tl[i] = u[i] - lb; tu[i] = ub - u[i]; ll[i] = 1.0; lu[i] = 1.0; }
     int it = 0, status = 2;
     double mu = 0;
     for (it = 0; it < max_iter; ++it) {
         mu = 0;
-        for (int i = 0; i < n; ++i) mu += ll[i] * (u[i] - lb) + lu[i] * (ub - u[i]);
+        for (int i = 0; i < n; ++i) mu += ll[i] * tl[i] + lu[i] * tu[i];
         mu /= (2.0 * n);
-        if (!(mu == mu)) { status = 3; break; }
+        if (!(mu == mu) || mu > 1e300) { status = 3; break; }
         if (mu < mu_tol) { status = 1; break; }
         /* predictor */
         for (int i = 0; i < n; ++i) {
-            double tl = u[i] - lb, tu = ub - u[i];
-            dR[i] = ll[i] / tl + lu[i] / tu;
+            dR[i] = ll[i] / tl[i] + lu[i] / tu[i];
             rt[i] = qp->r[i] - dR[i] * u[i];
         }
         riccati(qp, dR, rt, NULL, NULL, xw, ua);
         double alpha = 1.0;
         for (int i = 0; i < n; ++i) {
-            double tl = u[i] - lb, tu = ub - u[i], du = ua[i] - u[i];
-            dla[i] = -ll[i] - ll[i] / tl * du;
-            dua[i] = -lu[i] + lu[i] / tu * du;
-            if (du < 0) alpha = fmin(alpha, -tl / du);
-            if (du > 0) alpha = fmin(alpha, tu / du);
+            double du = ua[i] - u[i];
+            dla[i] = -ll[i] - ll[i] / tl[i] * du;
+            dua[i] = -lu[i] + lu[i] / tu[i] * du;
+            if (du < 0) alpha = fmin(alpha, -tl[i] / du);
+            if (du > 0) alpha = fmin(alpha, tu[i] / du);
             if (dla[i] < 0) alpha = fmin(alpha, -ll[i] / dla[i]);
             if (dua[i] < 0) alpha = fmin(alpha, -lu[i] / dua[i]);
         }
         double mua = 0;
         for (int i = 0; i < n; ++i) {
             double du = ua[i] - u[i];
-            mua += (ll[i] + alpha * dla[i]) * (u[i] + alpha * du - lb) + (lu[i] + alpha * dua[i]) * (ub - u[i] - alpha * du);
+            mua += (ll[i] + alpha * dla[i]) * (tl[i] + alpha * du) + (lu[i] + alpha * dua[i]) * (tu[i] - alpha * du);
         }
         mua /= (2.0 * n);
         double sigma = mua / mu; sigma = sigma * sigma * sigma;
         /* corrector */
         for (int i = 0; i < n; ++i) {
-            double tl = u[i] - lb, tu = ub - u[i], du = ua[i] - u[i];
+            double du = ua[i] - u[i];
             double cl = du * dla[i], cu = -du * dua[i];
-            rt[i] = qp->r[i] - dR[i] * u[i] - (sigma * mu - cl) / tl + (sigma * mu - cu) / tu;
+            rt[i] = qp->r[i] - dR[i] * u[i] - (sigma * mu - cl) / tl[i] + (sigma * mu - cu) / tu[i];
         }
         riccati(qp, dR, rt, NULL, NULL, xw, uc);
-        alpha = 1.0;
         double amax = 1e300;
         for (int i = 0; i < n; ++i) {
-            double tl = u[i] - lb, tu = ub - u[i], dua_ = ua[i] - u[i], du = uc[i] - u[i];
+            double dua_ = ua[i] - u[i], du = uc[i] - u[i];
             double cl = dua_ * dla[i], cu = -dua_ * dua[i];
-            double dl = (sigma * mu - cl) / tl - ll[i] - ll[i] / tl * du;
-            double dv = (sigma * mu - cu) / tu - lu[i] + lu[i] / tu * du;
+            double dl = (sigma * mu - cl) / tl[i] - ll[i] - ll[i] / tl[i] * du;
+            double dv = (sigma * mu - cu) / tu[i] - lu[i] + lu[i] / tu[i] * du;
             dla[i] = dl; dua[i] = dv;
-            if (du < 0) amax = fmin(amax, -tl / du);
-            if (du > 0) amax = fmin(amax, tu / du);
+            if (du < 0) amax = fmin(amax, -tl[i] / du);
+            if (du > 0) amax = fmin(amax, tu[i] / du);
             if (dl < 0) amax = fmin(amax, -ll[i] / dl);
             if (dv < 0) amax = fmin(amax, -lu[i] / dv);
         }
         alpha = fmin(1.0, 0.995 * amax);
         for (int i = 0; i < n; ++i) {
-            u[i] += alpha * (uc[i] - u[i]);
+            double du = uc[i] - u[i];
+            u[i] += alpha * du; tl[i] += alpha * du; tu[i] -= alpha * du;
             ll[i] += alpha * dla[i];
             lu[i] += alpha * dua[i];
         }
     }
     double *gu = (double *)malloc(sizeof(double) * n);
-    /* IPM answer and its KKT residual */
+    /* IPM answer (clipped into the box: the slacks, not u, carry the sub-ulp distance to a bound) and its KKT residual */
+    for (int i = 0; i < n; ++i) u[i] = fmin(fmax(u[i], lb), ub);
     qp_gradient(qp, u, xw, gu);
     double kkt = 0;
     for (int i = 0; i < n; ++i) kkt = fmax(kkt, fabs(gu[i] - ll[i] + lu[i]));
@@ -470,30 +473,43 @@ static int boxqp_solve(const qp_t *qp, double *xs, double *us, int *iters_out, d
     memcpy(us, u, sizeof(double) * n);
     memcpy(xs, xw, sizeof(double) * (N + 1) * NX);
     if (do_polish && status == 1) {
+        /* primal-dual active-set refinement started from the IPM's guess: solve the equality-constrained LQR with the
+           active inputs pinned; move violated free inputs onto their bound, release pinned inputs whose multiplier has
+           the wrong sign; stop when nothing changes => exact KKT point of the strictly convex QP. */
         unsigned char *fixed = (unsigned char *)calloc(n, 1);
         double *ufix = (double *)calloc(n, sizeof(double));
         for (int i = 0; i < n; ++i) {
-            double tl = u[i] - lb, tu = ub - u[i];
-            if (tl < ll[i]) { fixed[i] = 1; ufix[i] = lb; }
-            else if (tu < lu[i]) { fixed[i] = 2; ufix[i] = ub; }
+            if (tl[i] < ll[i]) { fixed[i] = 1; ufix[i] = lb; }
+            else if (tu[i] < lu[i]) { fixed[i] = 2; ufix[i] = ub; }
         }
-        riccati(qp, NULL, qp->r, fixed, ufix, xw, ua);
-        qp_gradient(qp, ua, xw, gu);
-        double viol = 0;
-        for (int i = 0; i < n; ++i) {
-            if (fixed[i] == 1) viol = fmax(viol, -gu[i]);
-            else if (fixed[i] == 2) viol = fmax(viol, gu[i]);
-            else { viol = fmax(viol, fabs(gu[i])); viol = fmax(viol, lb - ua[i]); viol = fmax(viol, ua[i] - ub); }
-        }
-        if (viol < 1e-9) {
-            status = 0; kkt = viol;
-            memcpy(us, ua, sizeof(double) * n);
-            memcpy(xs, xw, sizeof(double) * (N + 1) * NX);
+        for (int round = 0; round < 20; ++round) {
+            orc_last_rounds = round + 1;
+            riccati(qp, NULL, qp->r, fixed, ufix, xw, ua);
+            qp_gradient(qp, ua, xw, gu);
+            int changed = 0;
+            double viol = 0;
+            for (int i = 0; i < n; ++i) {
+                if (fixed[i] == 1) { if (gu[i] < -1e-12) { fixed[i] = 0; changed = 1; } }
+                else if (fixed[i] == 2) { if (gu[i] > 1e-12) { fixed[i] = 0; changed = 1; } }
+                else {
+                    viol = fmax(viol, fabs(gu[i]));
+                    if (ua[i] < lb) { fixed[i] = 1; ufix[i] = lb; changed = 1; }
+                    else if (ua[i] > ub) { fixed[i] = 2; ufix[i] = ub; changed = 1; }
+                }
+            }
+            if (!changed) {
+                if (viol < 1e-9) {
+                    status = 0; kkt = viol;
+                    memcpy(us, ua, sizeof(double) * n);
+                    memcpy(xs, xw, sizeof(double) * (N + 1) * NX);
+                }
+                break;
+            }
         }
         free(fixed); free(ufix);
     }
     *iters_out = it; *kkt_out = kkt;
-    free(u); free(ll); free(lu); free(dR); free(rt); free(ua); free(uc); free(xw); free(dla); free(dua); free(gu);
+    free(buf); free(gu);
     return status;
 }
 
