@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-sample-vehicles", type=int, default=0, help="0 = auto (about 15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cold", action="store_true", help="disable the active-set warm start (cold IPM every step)")
     return ap.parse_args()
 
 
@@ -188,7 +189,8 @@ def b200_arm(a):
     def make_loop():
         quad = Quadrotor3D(drag=True, batch=B, device=dev).set_hummingbird_params()
         gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B, device=dev) if M else None
-        opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision)
+        opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision,
+                             warm_start_rounds=(-1 if a.cold else 0))
         return ClosedLoop(quad, opt, torch.as_tensor(traj_np), torch.as_tensor(x0_np))
 
     def barrier():
@@ -241,16 +243,21 @@ def b200_arm(a):
     lat = np.array([evs[s].elapsed_time(evs[s + 1]) for s in range(a.steps)])
     # mean IPM iterations over a few sampled steps of a third short pass (host reads are outside any timed region)
     loop3 = make_loop()
-    n_ipm = []
+    n_ipm, n_rounds, n_warm_ok = [], [], []
     for s in range(a.warmup + min(a.steps, 20)):
         loop3.step()
         if s >= a.warmup:
-            n_ipm.append(float(loop3.opt.solver_status()[1].double().mean().item()))
+            it3 = loop3.opt.solver_status()[1].double()
+            n_ipm.append(float(it3.mean().item()))
+            n_rounds.append(float(loop3.opt.solver_rounds().double().mean().item()))
+            n_warm_ok.append(float((it3 == 0).double().mean().item()))
     n_ipm_mean = float(np.mean(n_ipm)) if n_ipm else n_ipm_last
+    n_rounds_mean = float(np.mean(n_rounds)) if n_rounds else 0.0
+    n_fact = n_ipm_mean + n_rounds_mean          # Riccati factorisations per vehicle-step
     peak = C.c_double()
     _capi.check(lib.qmpc_fma_peak(a.precision, C.byref(peak), _capi.stream_ptr()))
     ipm_ms = ms_ipm.value / max(cnt.value, 1)
-    ipm_flops = B * n_ipm_mean * 12067 * N            # algorithmic flops of the IPM kernel per launch (SURVEY §8d F_ipm)
+    ipm_flops = B * n_fact * 12067 * N                # algorithmic flops of the IPM kernel per launch (SURVEY §8d F_ipm per factorisation)
     achieved = ipm_flops / (ipm_ms * 1e-3) / 1e12 if ipm_ms > 0 else 0.0
     roofline = {"kernel": "qmpc_ipm_kernel", "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
                 "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
@@ -258,8 +265,10 @@ def b200_arm(a):
                                "MEASURED_PEAKS.json has no FMA figure",
                 "ms_per_launch": ipm_ms, "ms_linearize_per_launch": ms_lin.value / max(cnt.value, 1),
                 "share_of_step": ipm_ms / (ms / a.steps) if ms > 0 else None,
-                "n_ipm_mean": n_ipm_mean, "algorithmic_flops_per_vehicle_step": flops_per_step(N, M, n_ipm_mean),
-                "whole_step_tflops": value / world * flops_per_step(N, M, n_ipm_mean) / 1e12}
+                "n_ipm_mean": n_ipm_mean, "n_refine_rounds_mean": n_rounds_mean, "n_factorisations_mean": n_fact,
+                "warm_start_success_frac": float(np.mean(n_warm_ok)) if n_warm_ok else None,
+                "algorithmic_flops_per_vehicle_step": flops_per_step(N, M, n_fact),
+                "whole_step_tflops": value / world * flops_per_step(N, M, n_fact) / 1e12}
 
     # ---------------- e2e: host buffers in, host buffers out, through the Python API (pinned memory)
     e2e = None
@@ -322,7 +331,8 @@ def b200_arm(a):
                 "dtype": "f%d" % a.precision, "data": "synthetic", "config": workload_config(a, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
-                "solver": {"status_not_ok_last_step": bad, "ipm_iters_mean": n_ipm_mean}}
+                "solver": {"status_not_ok_last_step": bad, "ipm_iters_mean": n_ipm_mean, "refine_rounds_mean": n_rounds_mean,
+                           "warm_start": (not a.cold)}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

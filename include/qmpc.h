@@ -51,7 +51,7 @@ typedef struct {
     int device;          /* CUDA device ordinal                                                       */
     int ipm_max_iter;    /* <=0 -> 50                                                                  */
     int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 10, <0 -> off (pure IPM)     */
-    int reserved_;
+    int warm_start_rounds; /* refinement rounds tried first from the previous solve's active set: 0 -> 3, <0 -> off */
     double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32): complementarity target of the pure IPM     */
     double ipm_mu_switch; /* <=0 -> 1e-6 (fp64) / 1e-4 (fp32): IPM hands over to the refinement below this */
     double t_horizon;    /* tf ; dt = t_horizon / n_nodes (quad_opt.py:43)                            */
@@ -99,6 +99,10 @@ int qmpc_get_x(qmpc_handle_t h, double *x /*[B][N+1][13]*/, void *stream);
 int qmpc_get_u(qmpc_handle_t h, double *u /*[B][N][4]*/, void *stream);
 int qmpc_get_cost(qmpc_handle_t h, double *cost /*[B]*/, void *stream);
 int qmpc_get_status(qmpc_handle_t h, int *status /*[B]*/, int *iters /*[B]*/, void *stream);
+/* active-set refinement rounds of the last solve (warm-start rounds + rounds after the IPM), [B] */
+int qmpc_get_refine_rounds(qmpc_handle_t h, int *rounds /*[B]*/, void *stream);
+/* forget the active sets remembered for the warm start (the next solve starts from the cold IPM) */
+int qmpc_reset_warm_start(qmpc_handle_t h, void *stream);
 /* sum over vehicles of IPM iterations of the last solve (host value; synchronises `stream`) */
 int qmpc_iters_total(qmpc_handle_t h, long long *total, void *stream);
 

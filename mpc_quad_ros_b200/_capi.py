@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libqmpc.so")
+LIB_PATH = os.environ.get("QMPC_LIB", os.path.join(_HERE, "csrc", "libqmpc.so"))   # QMPC_LIB: kernel-tuning experiments only
 _LIB = None
 
 NX, NU, NY = 13, 4, 17
@@ -15,7 +15,7 @@ class QmpcConfig(C.Structure):
     """mirror of `qmpc_config` (include/qmpc.h)"""
     _fields_ = [
         ("batch", C.c_int), ("n_nodes", C.c_int), ("n_basis", C.c_int), ("precision", C.c_int),
-        ("device", C.c_int), ("ipm_max_iter", C.c_int), ("refine_max_rounds", C.c_int), ("reserved_", C.c_int),
+        ("device", C.c_int), ("ipm_max_iter", C.c_int), ("refine_max_rounds", C.c_int), ("warm_start_rounds", C.c_int),
         ("ipm_mu_tol", C.c_double), ("ipm_mu_switch", C.c_double), ("t_horizon", C.c_double),
         ("quad", C.c_double * 20), ("w_diag", C.c_double * 17), ("we_diag", C.c_double * 13),
         ("lbu", C.c_double), ("ubu", C.c_double), ("gp_theta", C.c_double * 9),

@@ -55,7 +55,8 @@ struct qmpc_solver {
     size_t rsz;                       // sizeof(real)
     double *x0 = nullptr, *yref = nullptr, *yref_e = nullptr, *alpha = nullptr, *xit = nullptr, *uit = nullptr;
     double *u0 = nullptr, *cost = nullptr, *gpX = nullptr, *xt = nullptr, *yt = nullptr;
-    int *status = nullptr, *iters = nullptr;
+    int *status = nullptr, *iters = nullptr, *rounds = nullptr;
+    unsigned char* act = nullptr;     // [B][4N] active sets remembered for the warm start
     void *W = nullptr, *fac = nullptr;
     const double* x0_src = nullptr;   // where the next solve reads x0 / alpha from (own buffers or bound ones)
     const double* alpha_src = nullptr;
@@ -100,7 +101,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     ALLOC(h->x0, B * NX * 8); ALLOC(h->yref, B * N * NY * 8); ALLOC(h->yref_e, B * NX * 8);
     ALLOC(h->alpha, B * 3 * (M ? M : 1) * 8); ALLOC(h->xit, B * (N + 1) * NX * 8); ALLOC(h->uit, B * N * NU * 8);
     ALLOC(h->u0, B * NU * 8); ALLOC(h->cost, B * 8); ALLOC(h->status, B * 4); ALLOC(h->iters, B * 4);
-    ALLOC(h->xt, B * 3 * 8); ALLOC(h->yt, B * 3 * 8);
+    ALLOC(h->xt, B * 3 * 8); ALLOC(h->yt, B * 3 * 8); ALLOC(h->rounds, B * 4); ALLOC(h->act, B * N * NU);
     ALLOC(h->W, B * N * WT * h->rsz); ALLOC(h->fac, B * N * FAC * h->rsz);
     ALLOC(h->gpX, 3 * (M ? M : 1) * 8);
 #undef ALLOC
@@ -109,6 +110,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     CU_TRY(cudaMemset(h->xit, 0, B * (N + 1) * NX * 8)); CU_TRY(cudaMemset(h->uit, 0, B * N * NU * 8));
     CU_TRY(cudaMemset(h->u0, 0, B * NU * 8)); CU_TRY(cudaMemset(h->cost, 0, B * 8));
     CU_TRY(cudaMemset(h->status, 0, B * 4)); CU_TRY(cudaMemset(h->iters, 0, B * 4));
+    CU_TRY(cudaMemset(h->rounds, 0, B * 4)); CU_TRY(cudaMemset(h->act, 255, B * N * NU));
     if (M) CU_TRY(cudaMemcpy(h->gpX, cfg->gp_X, 3 * M * 8, cudaMemcpyHostToDevice));
     h->x0_src = h->x0; h->alpha_src = h->alpha; h->alpha_stride = 3 * (int)M;
     const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N) * 8, smem32 = smem64 / 2;
@@ -125,7 +127,7 @@ int qmpc_destroy(qmpc_handle_t h)
     if (!h) return QMPC_OK;
     cudaSetDevice(h->cfg.device);
     void* ps[] = {h->x0, h->yref, h->yref_e, h->alpha, h->xit, h->uit, h->u0, h->cost, h->status, h->iters,
-                  h->W, h->fac, h->gpX, h->xt, h->yt};
+                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act};
     for (void* p : ps) if (p) cudaFree(p);
     delete h;
     return QMPC_OK;
@@ -223,7 +225,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
     fill_ipm_args(h->cfg, ia);
     ia.x0 = h->x0_src; ia.yref = h->yref; ia.yref_e = h->yref_e; ia.xit = h->xit; ia.uit = h->uit;
     ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
-    ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters;
+    ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters; ia.rounds = h->rounds; ia.act = h->act;
     const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real);
     qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
     LAUNCH_CHECK();
@@ -264,6 +266,17 @@ int qmpc_get_status(qmpc_handle_t h, int* status, int* iters, void* stream)
     if (!h) return fail(QMPC_ERR_ARG, "null handle");
     if (status) { int rc = copy_dd(status, h->status, (size_t)h->cfg.batch * 4, stream); if (rc) return rc; }
     if (iters) { int rc = copy_dd(iters, h->iters, (size_t)h->cfg.batch * 4, stream); if (rc) return rc; }
+    return QMPC_OK;
+}
+int qmpc_get_refine_rounds(qmpc_handle_t h, int* rounds, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    return copy_dd(rounds, h->rounds, (size_t)h->cfg.batch * 4, stream);
+}
+int qmpc_reset_warm_start(qmpc_handle_t h, void* stream)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    CU_TRY(cudaMemsetAsync(h->act, 255, (size_t)h->cfg.batch * h->cfg.n_nodes * NU, S(stream)));
     return QMPC_OK;
 }
 int qmpc_iters_total(qmpc_handle_t h, long long* total, void* stream)

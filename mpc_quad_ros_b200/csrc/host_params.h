@@ -28,7 +28,7 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
 }
 
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
-inline int ipm_smem_reals(int N) { return SM_VEC + SM_NVEC * 4 * N + (N + 1) * 13 + 9; }
+inline int ipm_smem_reals(int N) { return (SM_VEC + SM_NVEC * 4 * N + (N + 1) * 13 + 9) & ~1; }
 
 template <typename real>
 inline void fill_lin_args(const qmpc_config& c, LinArgs<real>& a)
@@ -53,6 +53,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.mu_switch = real(c.ipm_mu_switch > 0 ? c.ipm_mu_switch : (f64 ? 1e-6 : 1e-4));
     a.refine_gtol = real(f64 ? 1e-12 : 1e-5);
     a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? 10 : c.refine_max_rounds);
+    a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 3 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
 }
 

@@ -125,20 +125,41 @@ struct IpmArgs {
     real mu_switch;                // complementarity at which the IPM hands over to the active-set refinement
     real refine_gtol;              // sign tolerance on the multipliers of pinned inputs
     int max_iter;
-    int max_refine;                // 0 = pure IPM down to mu_tol
+    int max_refine;                // refinement rounds after the IPM; 0 = pure IPM down to mu_tol
+    int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
     int smem_per_warp;             // reals
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
     const double* yref_e;          // [B][13]
     double* xit;                   // [B][N+1][13]  in/out
     double* uit;                   // [B][N][4]     in/out
-    const real* W;                 // [B][N][13][16]
+    const real* W;                 // [B][N][13][16] (+1 padding tile)
     real* fac;                     // [B][N][FAC]
+    unsigned char* act;            // [B][4N] active set of the previous solve: 0 free, 1 lower, 2 upper, 255 unknown
     double* u0;                    // [B][4]
     double* cost;                  // [B]
     int* status;                   // [B]
-    int* iters;                    // [B]
+    int* iters;                    // [B]  IPM iterations
+    int* rounds;                   // [B]  active-set refinement rounds (warm + after the IPM)
 };
+
+template <typename real> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+// two consecutive reals with one load (p must be aligned to 2 reals)
+template <typename real>
+__device__ __forceinline__ void ld2(const real* p, real& a, real& b)
+{
+    const typename Vec2<real>::type v = *reinterpret_cast<const typename Vec2<real>::type*>(p);
+    a = v.x; b = v.y;
+}
+template <typename real>
+__device__ __forceinline__ void ldg2(const real* p, real& a, real& b)
+{
+    const typename Vec2<real>::type v = __ldg(reinterpret_cast<const typename Vec2<real>::type*>(p));
+    a = v.x; b = v.y;
+}
 
 template <typename real>
 struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal
@@ -173,7 +194,12 @@ struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal
     }
     __device__ __forceinline__ void load(const real* p)
     {
-        l10 = p[0]; l20 = p[1]; l21 = p[2]; l30 = p[3]; l31 = p[4]; l32 = p[5]; i0 = p[6]; i1 = p[7]; i2 = p[8]; i3 = p[9];
+        real a, b;
+        ld2(p, a, b); l10 = a; l20 = b;
+        ld2(p + 2, a, b); l21 = a; l30 = b;
+        ld2(p + 4, a, b); l31 = a; l32 = b;
+        ld2(p + 6, a, b); i0 = a; i1 = b;
+        ld2(p + 8, a, b); i2 = a; i3 = b;
     }
 };
 
@@ -182,8 +208,14 @@ __device__ __forceinline__ real dot4(const real* a, const real* b)
 {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
 }
+template <typename real>
+__device__ __forceinline__ real sel4(const real* v, int i)   // v[i] for a register array and a run-time i
+{
+    return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
+}
 
-// per-warp shared-memory carve-up (offsets in reals)
+// per-warp shared-memory carve-up (offsets in reals; every block starts on an even offset)
+constexpr int PS = 14;         // row stride of P (even: rows are read two reals at a time)
 constexpr int SM_P = 0;        // 14 x 14 (row 13 stays zero)
 constexpr int SM_PV = 200;     // 16  costate offset p
 constexpr int SM_WV = 216;     // 16  forward vector: u(4), z(10), one, zero
@@ -214,64 +246,90 @@ struct WarpCtx {
         for (int i = 0; i < NX; ++i) w[i] = __ldg(t + i * 16);
     }
 
-    // backward Riccati sweep with factorisation; gradient: rt (inputs), q column (states), b column (offset)
+    // Backward Riccati sweep with factorisation.  Gradient: rt (inputs), q column (states), b column (offset).
     // FIXED: inputs flagged in fx are pinned at fv (exact elimination: their rows/columns of M_uu, M_ux become
-    // identity/zero and M[:,a] fv_a moves into the gradient).
+    // identity/zero and M[:,a] fv_a moves into the gradient); rt = rdel and dR = 0 in that mode.
+    //
+    // lane = (h, j): tile column j (0..3 B, 4..13 A', 14 b, 15 q); half h owns rows 7h..7h+6 of y = P w_j and
+    // rows 8h..8h+7 of this column of M = W^T P W.
     template <bool FIXED>
     __device__ void backward_full()
     {
         for (int idx = lane; idx < 196; idx += 32) P[idx] = 0;
         __syncwarp();
         if (lane < NX) {
-            P[lane * 14 + lane] = a.QNd[lane];
+            P[lane * PS + lane] = a.QNd[lane];
             pv[lane] = a.QNd[lane] * real(xit[(size_t)N * NX + lane] - yref_e[lane]);
         }
         __syncwarp();
-        real w[NX], wn[NX];
-        load_col(N - 1, w);
-        const int r0 = h * 7;
+        const int r0 = 7 * h, o0 = 7 - r0, cb = 8 * h;
         for (int k = N - 1; k >= 0; --k) {
-            if (k > 0) load_col(k - 1, wn);
             const real* tile = Wv + (size_t)k * WT;
+            real w[NX];
+            load_col(k, w);
             const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
-            // y = P w  (own half of the rows), then exchange halves
-            real y[7], yf[NX];
+            // y = P w: rows r0..r0+6 here, rows o0..o0+6 from the partner lane (row 13 is the zero padding row)
+            real ym[7], yo[7];
 #pragma unroll
             for (int ii = 0; ii < 7; ++ii) {
-                const real* pr = P + (r0 + ii) * 14;
-                real s = 0;
+                const real* pr = P + (r0 + ii) * PS;
+                real s0 = 0, s1 = 0;
 #pragma unroll
-                for (int c = 0; c < NX; ++c) s += pr[c] * w[c];
-                y[ii] = s;
+                for (int c = 0; c < 12; c += 2) {
+                    real p0, p1;
+                    ld2(pr + c, p0, p1);
+                    s0 += p0 * w[c]; s1 += p1 * w[c + 1];
+                }
+                ym[ii] = s0 + s1 + pr[12] * w[12];
             }
 #pragma unroll
-            for (int ii = 0; ii < 7; ++ii) {
-                const real yo = __shfl_xor_sync(FULL, y[ii], 16);
-                const real lo = h ? yo : y[ii], hi = h ? y[ii] : yo;
-                yf[ii] = lo;
-                if (ii < 6) yf[7 + ii] = hi;
-            }
-            if (lane == 14) {
+            for (int ii = 0; ii < 7; ++ii) yo[ii] = __shfl_xor_sync(FULL, ym[ii], 16);
+            if (lane == 14) {                      // h = P b + p  (lane 14: r0 = 0, o0 = 7)
 #pragma unroll
-                for (int i = 0; i < NX; ++i) hv[i] = yf[i] + pv[i];
-            }
-            // M rows (dense tile columns r0..r0+6) of this lane's column
-            real m[7];
+                for (int ii = 0; ii < 7; ++ii) hv[ii] = ym[ii] + pv[ii];
 #pragma unroll
-            for (int ii = 0; ii < 7; ++ii) {
-                const int i = r0 + ii;
-                real s = 0;
-#pragma unroll
-                for (int c = 0; c < NX; ++c) s += __ldg(tile + c * 16 + i) * yf[c];
-                if (i == j) s += (j < 4) ? (a.Rd[j] + dR[k * 4 + j]) : a.Qd[j - 1];
-                m[ii] = s;
+                for (int ii = 0; ii < 6; ++ii) hv[7 + ii] = yo[ii] + pv[7 + ii];
             }
-            __syncwarp();
+            // rows cb..cb+7 of this lane's column of M:  M[i][j] = sum_r W[r][i] y[r]
+            real m[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) m[ii] = 0;
+#pragma unroll
+            for (int kk = 0; kk < 7; ++kk) {
+                const real* tr = tile + (r0 + kk < NX ? r0 + kk : NX - 1) * 16 + cb;   // y is 0 on the padding row
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    real t0, t1;
+                    ldg2(tr + c, t0, t1);
+                    m[c] += t0 * ym[kk]; m[c + 1] += t1 * ym[kk];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 7; ++kk) {
+                const real* tr = tile + (o0 + kk < NX ? o0 + kk : NX - 1) * 16 + cb;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    real t0, t1;
+                    ldg2(tr + c, t0, t1);
+                    m[c] += t0 * yo[kk]; m[c + 1] += t1 * yo[kk];
+                }
+            }
+            if (j < 14 && (j >> 3) == h) {         // cost diagonal
+                const real dg = j < 4 ? a.Rd[j] + (FIXED ? real(0) : dR[k * 4 + j]) : a.Qd[j - 1];
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) if (ii == (j & 7)) m[ii] += dg;
+            }
+            __syncwarp();                          // hv visible; every read of the old P is done
             real g = 0;
 #pragma unroll
-            for (int c = 0; c < NX; ++c) g += w[c] * hv[c];
-            g += (j < 4) ? rt[k * 4 + j] : qj;
-            real mu4[4];                         // rows 0..3 (inputs) of this lane's column; they live in the h=0 half
+            for (int c = 0; c < 12; c += 2) {
+                real h0, h1;
+                ld2(hv + c, h0, h1);
+                g += w[c] * h0 + w[c + 1] * h1;
+            }
+            g += w[12] * hv[12];
+            g += (j < 4) ? (FIXED ? rdel[k * 4 + j] : rt[k * 4 + j]) : qj;
+            real mu4[4];                           // rows 0..3 (inputs) of this lane's column; they live in the h=0 half
 #pragma unroll
             for (int aa = 0; aa < 4; ++aa) mu4[aa] = __shfl_sync(FULL, m[aa], j);
             real fxa[4] = {0, 0, 0, 0}, fva[4] = {0, 0, 0, 0};
@@ -282,7 +340,7 @@ struct WarpCtx {
                 for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) g += mu4[aa] * fva[aa];   // M[:,a] fv_a -> gradient
             }
             if (lane < 4) {
-                const bool mefix = FIXED && (lane == 0 ? fxa[0] : (lane == 1 ? fxa[1] : (lane == 2 ? fxa[2] : fxa[3]))) != real(0);
+                const bool mefix = FIXED && sel4(fxa, lane) != real(0);
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) {
                     real v = m[aa];
@@ -290,26 +348,28 @@ struct WarpCtx {
                     cs[aa * 4 + lane] = v;
                 }
 #pragma unroll
-                for (int pi = 0; pi < 3; ++pi) cs[16 + pi * 4 + lane] = yf[pi];
+                for (int pi = 0; pi < 3; ++pi) cs[16 + pi * 4 + lane] = ym[pi];    // M[p_i][a] = (P w_a)[p_i]
                 cs[28 + lane] = mefix ? real(0) : g;
             }
             __syncwarp();
             Chol4<real> L;
             real lg[4], lp[3][4], lj[4];
-            real gpc[3] = {0, 0, 0};             // gradient correction of the position rows from pinned inputs
+            real gpc[3] = {0, 0, 0};               // gradient correction of the position rows from pinned inputs
             {
                 real Muu[16];
 #pragma unroll
-                for (int t = 0; t < 16; ++t) Muu[t] = cs[t];
+                for (int t = 0; t < 16; t += 2) ld2(cs + t, Muu[t], Muu[t + 1]);
                 L.factor(Muu);
-                L.fsolve(cs + 28, lg);
+                real gu[4];
+                ld2(cs + 28, gu[0], gu[1]); ld2(cs + 30, gu[2], gu[3]);
+                L.fsolve(gu, lg);
 #pragma unroll
                 for (int pi = 0; pi < 3; ++pi) {
                     real mpu[4];
+                    ld2(cs + 16 + pi * 4, mpu[0], mpu[1]); ld2(cs + 18 + pi * 4, mpu[2], mpu[3]);
+                    if (FIXED) {
 #pragma unroll
-                    for (int aa = 0; aa < 4; ++aa) {
-                        mpu[aa] = cs[16 + pi * 4 + aa];
-                        if (FIXED && fxa[aa] != real(0)) { gpc[pi] += mpu[aa] * fva[aa]; mpu[aa] = 0; }
+                        for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) { gpc[pi] += mpu[aa] * fva[aa]; mpu[aa] = 0; }
                     }
                     L.fsolve(mpu, lp[pi]);
                 }
@@ -319,7 +379,7 @@ struct WarpCtx {
                 for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) mu4[aa] = 0;
             }
             L.fsolve(mu4, lj);
-            real lpme[4];                       // l_p of "my" position state (lanes 0..2)
+            real lpme[4];                          // l_p of "my" position state (lanes 0..2)
 #pragma unroll
             for (int aa = 0; aa < 4; ++aa) lpme[aa] = j == 0 ? lp[0][aa] : (j == 1 ? lp[1][aa] : lp[2][aa]);
             if (h == 0) {
@@ -331,16 +391,20 @@ struct WarpCtx {
                 if (j >= 4 && j < 14) {
                     const int sj = j - 1;
 #pragma unroll
-                    for (int ii = 0; ii < 7; ++ii) {
-                        const int i = r0 + ii;
-                        if (i >= 4 && i < 14) P[(i - 1) * 14 + sj] = m[ii] - dot4(Ls + i * 4, lj);
+                    for (int ii = 0; ii < 8; ++ii) {
+                        const int i = cb + ii;
+                        if (i >= 4 && i < 14) {
+                            real l0, l1, l2, l3;
+                            ld2(Ls + i * 4, l0, l1); ld2(Ls + i * 4 + 2, l2, l3);
+                            P[(i - 1) * PS + sj] = m[ii] - (l0 * lj[0] + l1 * lj[1] + l2 * lj[2] + l3 * lj[3]);
+                        }
                     }
                     if (h == 0) {
 #pragma unroll
                         for (int pi = 0; pi < 3; ++pi) {
-                            const real v = yf[pi] - dot4(lp[pi], lj);
-                            P[pi * 14 + sj] = v;
-                            P[sj * 14 + pi] = v;
+                            const real v = ym[pi] - dot4(lp[pi], lj);
+                            P[pi * PS + sj] = v;
+                            P[sj * PS + pi] = v;
                         }
                         pv[sj] = g - dot4(lj, lg);
                     }
@@ -348,7 +412,7 @@ struct WarpCtx {
                 if (lane < 3) {
 #pragma unroll
                     for (int pi = 0; pi < 3; ++pi)
-                        P[pi * 14 + lane] += ((pi == lane) ? a.Qd[lane] : real(0)) - dot4(lp[pi], lpme);
+                        P[pi * PS + lane] += ((pi == lane) ? a.Qd[lane] : real(0)) - dot4(lp[pi], lpme);
                     pv[lane] = hv[lane] + qj + (lane == 0 ? gpc[0] : (lane == 1 ? gpc[1] : gpc[2])) - dot4(lpme, lg);
                 }
             }
@@ -368,8 +432,6 @@ struct WarpCtx {
                 }
             }
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < NX; ++i) w[i] = wn[i];
         }
     }
 
@@ -378,21 +440,22 @@ struct WarpCtx {
     {
         if (lane < 16) pv[lane] = 0;
         __syncwarp();
-        real w[NX], wn[NX];
-        load_col(N - 1, w);
         for (int k = N - 1; k >= 0; --k) {
-            if (k > 0) load_col(k - 1, wn);
+            real w[NX];
+            load_col(k, w);
             const real* f = facv + (size_t)k * FAC;
             Chol4<real> L;
             L.load(f + 56);
             real lx[4] = {0, 0, 0, 0};
-            if (sidx >= 0) {
-#pragma unroll
-                for (int aa = 0; aa < 4; ++aa) lx[aa] = f[sidx * 4 + aa];
-            }
+            if (sidx >= 0) { ld2(f + sidx * 4, lx[0], lx[1]); ld2(f + sidx * 4 + 2, lx[2], lx[3]); }
             real g = 0;
 #pragma unroll
-            for (int c = 0; c < NX; ++c) g += w[c] * pv[c];
+            for (int c = 0; c < 12; c += 2) {
+                real h0, h1;
+                ld2(pv + c, h0, h1);
+                g += w[c] * h0 + w[c + 1] * h1;
+            }
+            g += w[12] * pv[12];
             if (j < 4) g += rt[k * 4 + j];
             real gu[4], lgc[4];
 #pragma unroll
@@ -409,8 +472,6 @@ struct WarpCtx {
                 }
             }
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < NX; ++i) w[i] = wn[i];
         }
     }
 
@@ -419,15 +480,19 @@ struct WarpCtx {
     {
         if (lane < NX) pv[lane] = a.QNd[lane] * (xtr[(size_t)N * NX + lane] + real(xit[(size_t)N * NX + lane] - yref_e[lane]));
         __syncwarp();
-        real w[NX], wn[NX];
-        load_col(N - 1, w);
         for (int k = N - 1; k >= 0; --k) {
-            if (k > 0) load_col(k - 1, wn);
+            real w[NX];
+            load_col(k, w);
             const real* tile = Wv + (size_t)k * WT;
             const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
             real g = 0;
 #pragma unroll
-            for (int c = 0; c < NX; ++c) g += w[c] * pv[c];
+            for (int c = 0; c < 12; c += 2) {
+                real h0, h1;
+                ld2(pv + c, h0, h1);
+                g += w[c] * h0 + w[c + 1] * h1;
+            }
+            g += w[12] * pv[12];
             const real xk = sidx >= 0 ? xtr[k * NX + sidx] : real(0);
             const real pold = j < 3 ? pv[j] : real(0);
             __syncwarp();
@@ -437,21 +502,15 @@ struct WarpCtx {
                 else if (j < 3) pv[j] = pold + a.Qd[j] * xk + qj;
             }
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < NX; ++i) w[i] = wn[i];
         }
     }
 
-    // Primal-dual active-set refinement from the IPM's guess of the active set.  Each round solves the LQR with the
-    // active inputs pinned (one factorisation + one forward sweep) and checks the multipliers with an adjoint sweep.
+    // Primal-dual active-set rounds from the active set in fx.  Each round solves the LQR with the active inputs
+    // pinned (one factorisation + one forward sweep) and checks the multipliers with an adjoint sweep.
     // Returns true when the active set is self-consistent: usol then holds the exact minimiser of the box-QP.
-    __device__ bool refine_active_set(real lb, real ub)
+    __device__ bool refine_rounds(real lb, real ub, int max_rounds, int& rounds)
     {
-        for (int e = lane; e < E; e += 32) {
-            fx[e] = tl[e] < ll[e] ? real(1) : (tu[e] < lu[e] ? real(2) : real(0));
-            dR[e] = 0; rt[e] = rdel[e];
-        }
-        for (int round = 0; round < a.max_refine; ++round) {
+        for (int round = 0; round < max_rounds; ++round) {
             for (int e = lane; e < E; e += 32) fv[e] = fx[e] == real(1) ? lb - ubar[e] : (fx[e] == real(2) ? ub - ubar[e] : real(0));
             __syncwarp();
             backward_full<true>();
@@ -459,6 +518,7 @@ struct WarpCtx {
             __syncwarp();
             backward_adjoint();
             __syncwarp();
+            ++rounds;
             int changed = 0;
             for (int e = lane; e < E; e += 32) {
                 const real f = fx[e], un = ubar[e] + usol[e], gr = grad[e];
@@ -477,6 +537,7 @@ struct WarpCtx {
     //                 MODE 1: feedback with lgc, homogeneous (corrector increment, writes usol)
     //                 MODE 2: open loop with usol, offset b; writes the new iterate and returns the objective
     //                 FIXED (with MODE 0): pinned inputs take fv; the state trajectory is kept in xtr for the adjoint
+    // lane = (h, i): row i of the tile (state i), half h multiplies tile columns 8h..8h+7.
     template <int MODE, bool FIXED = false>
     __device__ real forward()
     {
@@ -495,43 +556,45 @@ struct WarpCtx {
         __syncwarp();
         const int irow = j < NX ? j : NX - 1;
         for (int k = 0; k < N; ++k) {
-            const real* tile = Wv + (size_t)k * WT;
+            const real* tr = Wv + (size_t)k * WT + irow * 16 + h * 8;
             real wr[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) wr[c] = __ldg(tile + irow * 16 + h * 8 + c);
+            for (int c = 0; c < 8; c += 2) ldg2(tr + c, wr[c], wr[c + 1]);
             real u[4];
             if (MODE != 2) {
                 const real* f = facv + (size_t)k * FAC;
                 Chol4<real> L;
                 L.load(f + 56);
                 const real xo = j < 3 ? xp[j] : (j < NX ? wv[j + 1] : real(0));
-                real v[4];
+                real v[4] = {0, 0, 0, 0};
+                const int src = j < NX ? j * 4 : (MODE == 0 ? 52 : 66);
+                if (j <= NX) { ld2(f + src, v[0], v[1]); ld2(f + src + 2, v[2], v[3]); }
+                const real sc = j < NX ? xo : real(1);
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) {
-                    real t = 0;
-                    if (j < NX) t = f[j * 4 + aa] * xo;
-                    else if (j == 13) t = f[(MODE == 0 ? 52 : 66) + aa];
-                    v[aa] = half_sum(hmask, t);
-                }
+                for (int aa = 0; aa < 4; ++aa) v[aa] = half_sum(hmask, v[aa] * sc);
                 L.bsolve_neg(v, u);
                 if (FIXED) {
 #pragma unroll
                     for (int aa = 0; aa < 4; ++aa) if (fx[k * 4 + aa] != real(0)) u[aa] = fv[k * 4 + aa];
                 }
             } else {
-#pragma unroll
-                for (int aa = 0; aa < 4; ++aa) u[aa] = usol[k * 4 + aa];
+                ld2(usol + k * 4, u[0], u[1]); ld2(usol + k * 4 + 2, u[2], u[3]);
             }
             __syncwarp();                       // everyone has read the old state
             if (lane < 4) {
-                const real ul = lane == 0 ? u[0] : (lane == 1 ? u[1] : (lane == 2 ? u[2] : u[3]));
+                const real ul = sel4(u, lane);
                 wv[lane] = ul;
                 if (MODE != 2) usol[k * 4 + lane] = ul;
             }
             __syncwarp();
-            real acc = 0;
+            real acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc += wr[c] * wv[h * 8 + c];
+            for (int c = 0; c < 8; c += 2) {
+                real v0, v1;
+                ld2(wv + h * 8 + c, v0, v1);
+                acc0 += wr[c] * v0; acc1 += wr[c + 1] * v1;
+            }
+            real acc = acc0 + acc1;
             acc += __shfl_xor_sync(FULL, acc, 16);
             if (j < 3) acc += xp[j];
             __syncwarp();
@@ -548,7 +611,7 @@ struct WarpCtx {
                     cost += real(0.5) * wgt * e * e;
                 }
             } else if (MODE == 2 && h == 1 && j < 4) {
-                const real e = real(double(ubar[k * 4 + j]) + double(u[j == 0 ? 0 : (j == 1 ? 1 : (j == 2 ? 2 : 3))]) - yref[(size_t)k * NY + NX + j]);
+                const real e = real(double(ubar[k * 4 + j]) + double(sel4(u, j)) - yref[(size_t)k * NY + NX + j]);
                 cost += real(0.5) * a.Rd[j] * e * e;
             }
             __syncwarp();
@@ -557,8 +620,12 @@ struct WarpCtx {
     }
 };
 
+#ifndef QMPC_IPM_MIN_BLOCKS
+#define QMPC_IPM_MIN_BLOCKS 4
+#endif
+
 template <typename real, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
+__global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_BLOCKS) qmpc_ipm_kernel(IpmArgs<real> a)
 {
     QMPC_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -584,102 +651,124 @@ __global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
     c.yref_e = a.yref_e + (size_t)ocp * NX;
     c.xit = a.xit + (size_t)ocp * (N + 1) * NX;
     c.uit = a.uit + (size_t)ocp * N * NU;
+    unsigned char* act = a.act + (size_t)ocp * E;
 
     const real lb = a.lb, ub = a.ub;
     for (int e = lane; e < E; e += 32) {
         const real ub_ = real(c.uit[e]);
         c.ubar[e] = ub_;
         c.rdel[e] = a.Rd[e & 3] * (ub_ - real(c.yref[(size_t)(e >> 2) * NY + NX + (e & 3)]));
-        const real u0 = real(0.5) * (lb + ub);
-        c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0;     // slacks are carried, never recomputed from u
-        c.ll[e] = 1; c.lu[e] = 1;
     }
     __syncwarp();
 
-    int it = 0, status = QMPC_STATUS_MAXITER_;
+    int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
     bool exact = false;
-    bool refine = a.max_refine > 0;
-    real target = refine ? a.mu_switch : a.mu_tol;
-    const real inv2E = real(1) / real(2 * E);
-    while (true) {
-        real s = 0;
-        for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
-        const real mu = warp_sum(s) * inv2E;
-        if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
-        if (mu < target) {
-            if (refine) {
-                if (c.refine_active_set(lb, ub)) { status = QMPC_STATUS_OK_; exact = true; break; }
-                refine = false; target = a.mu_tol;           // inconsistent active set: resume the IPM to the tight tolerance
-                if (mu < target) { status = QMPC_STATUS_OK_; break; }
-            } else { status = QMPC_STATUS_OK_; break; }
-        }
-        if (it >= a.max_iter) break;
-        // ---- predictor
-        for (int e = lane; e < E; e += 32) {
-            const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];
-            c.dR[e] = d;
-            c.rt[e] = c.rdel[e] - d * (c.ucur[e] - c.ubar[e]);
-        }
-        __syncwarp();
-        c.template backward_full<false>();
-        c.template forward<0>();
-        __syncwarp();
-        real amin = 1;
-        for (int e = lane; e < E; e += 32) {
-            const real tl = c.tl[e], tu = c.tu[e];
-            const real du = c.ubar[e] + c.usol[e] - c.ucur[e];
-            const real dl = -c.ll[e] - c.ll[e] / tl * du;
-            const real dv = -c.lu[e] + c.lu[e] / tu * du;
-            c.ua[e] = c.usol[e];
-            c.cl[e] = du * dl; c.cu[e] = -du * dv;
-            c.rt[e] = dl; c.dR[e] = dv;
-            if (du < 0) amin = fmin(amin, -tl / du);
-            if (du > 0) amin = fmin(amin, tu / du);
-            if (dl < 0) amin = fmin(amin, -c.ll[e] / dl);
-            if (dv < 0) amin = fmin(amin, -c.lu[e] / dv);
-        }
-        const real aaff = warp_min(amin);
-        s = 0;
-        for (int e = lane; e < E; e += 32) {
-            const real du = c.ubar[e] + c.ua[e] - c.ucur[e];
-            s += (c.ll[e] + aaff * c.rt[e]) * (c.tl[e] + aaff * du) + (c.lu[e] + aaff * c.dR[e]) * (c.tu[e] - aaff * du);
-        }
-        const real muaff = warp_sum(s) * inv2E;
-        real sigma = muaff / mu; sigma = sigma * sigma * sigma;
-        const real smu = sigma * mu;
-        // ---- corrector (increment on top of the predictor solution)
-        for (int e = lane; e < E; e += 32)
-            c.rt[e] = -(smu - c.cl[e]) / c.tl[e] + (smu - c.cu[e]) / c.tu[e];
-        __syncwarp();
-        c.backward_vec();
-        c.template forward<1>();
-        __syncwarp();
-        real amax = real(1e30);
-        for (int e = lane; e < E; e += 32) {
-            const real tl = c.tl[e], tu = c.tu[e];
-            const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
-            const real dl = (smu - c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
-            const real dv = (smu - c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
-            c.usol[e] = du; c.rt[e] = dl; c.dR[e] = dv;
-            if (du < 0) amax = fmin(amax, -tl / du);
-            if (du > 0) amax = fmin(amax, tu / du);
-            if (dl < 0) amax = fmin(amax, -c.ll[e] / dl);
-            if (dv < 0) amax = fmin(amax, -c.lu[e] / dv);
-        }
-        const real alpha = fmin(real(1), real(0.995) * warp_min(amax));
-        for (int e = lane; e < E; e += 32) {
-            const real du = alpha * c.usol[e];
-            c.ucur[e] += du; c.tl[e] += du; c.tu[e] -= du;
-            c.ll[e] += alpha * c.rt[e];
-            c.lu[e] += alpha * c.dR[e];
-        }
-        ++it;
+    // ---- 1. warm start: the active set of the previous solve is usually still right (RTI does not shift the horizon)
+    if (a.warm_rounds > 0) {
+        int known = 1;
+        for (int e = lane; e < E; e += 32) { const unsigned char f = act[e]; if (f > 2) known = 0; c.fx[e] = real(f <= 2 ? f : 0); }
+        known = -warp_max(-known);
+        if (known && c.refine_rounds(lb, ub, a.warm_rounds, rounds)) { exact = true; status = QMPC_STATUS_OK_; }
     }
-    // ---- full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
+    // ---- 2. Mehrotra predictor-corrector IPM (cold start), handing over to the active-set refinement at mu_switch
+    if (!exact) {
+        for (int e = lane; e < E; e += 32) {
+            const real u0 = real(0.5) * (lb + ub);
+            c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0;     // slacks are carried, never recomputed from u
+            c.ll[e] = 1; c.lu[e] = 1;
+        }
+        bool refine = a.max_refine > 0;
+        real target = refine ? a.mu_switch : a.mu_tol;
+        const real inv2E = real(1) / real(2 * E);
+        while (true) {
+            real s = 0;
+            for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
+            const real mu = warp_sum(s) * inv2E;
+            if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
+            if (mu < target) {
+                if (refine) {
+                    for (int e = lane; e < E; e += 32)
+                        c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
+                    if (c.refine_rounds(lb, ub, a.max_refine, rounds)) { status = QMPC_STATUS_OK_; exact = true; break; }
+                    refine = false; target = a.mu_tol;       // inconsistent active set: resume the IPM to the tight tolerance
+                    if (mu < target) { status = QMPC_STATUS_OK_; break; }
+                } else { status = QMPC_STATUS_OK_; break; }
+            }
+            if (it >= a.max_iter) break;
+            // predictor
+            for (int e = lane; e < E; e += 32) {
+                const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];
+                c.dR[e] = d;
+                c.rt[e] = c.rdel[e] - d * (c.ucur[e] - c.ubar[e]);
+            }
+            __syncwarp();
+            c.template backward_full<false>();
+            c.template forward<0>();
+            __syncwarp();
+            real amin = 1;
+            for (int e = lane; e < E; e += 32) {
+                const real tl = c.tl[e], tu = c.tu[e];
+                const real du = c.ubar[e] + c.usol[e] - c.ucur[e];
+                const real dl = -c.ll[e] - c.ll[e] / tl * du;
+                const real dv = -c.lu[e] + c.lu[e] / tu * du;
+                c.ua[e] = c.usol[e];
+                c.cl[e] = du * dl; c.cu[e] = -du * dv;
+                c.rt[e] = dl; c.dR[e] = dv;
+                if (du < 0) amin = fmin(amin, -tl / du);
+                if (du > 0) amin = fmin(amin, tu / du);
+                if (dl < 0) amin = fmin(amin, -c.ll[e] / dl);
+                if (dv < 0) amin = fmin(amin, -c.lu[e] / dv);
+            }
+            const real aaff = warp_min(amin);
+            s = 0;
+            for (int e = lane; e < E; e += 32) {
+                const real du = c.ubar[e] + c.ua[e] - c.ucur[e];
+                s += (c.ll[e] + aaff * c.rt[e]) * (c.tl[e] + aaff * du) + (c.lu[e] + aaff * c.dR[e]) * (c.tu[e] - aaff * du);
+            }
+            const real muaff = warp_sum(s) * inv2E;
+            real sigma = muaff / mu; sigma = sigma * sigma * sigma;
+            const real smu = sigma * mu;
+            // corrector (increment on top of the predictor solution)
+            for (int e = lane; e < E; e += 32)
+                c.rt[e] = -(smu - c.cl[e]) / c.tl[e] + (smu - c.cu[e]) / c.tu[e];
+            __syncwarp();
+            c.backward_vec();
+            c.template forward<1>();
+            __syncwarp();
+            real amax = real(1e30);
+            for (int e = lane; e < E; e += 32) {
+                const real tl = c.tl[e], tu = c.tu[e];
+                const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
+                const real dl = (smu - c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
+                const real dv = (smu - c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
+                c.usol[e] = du; c.rt[e] = dl; c.dR[e] = dv;
+                if (du < 0) amax = fmin(amax, -tl / du);
+                if (du > 0) amax = fmin(amax, tu / du);
+                if (dl < 0) amax = fmin(amax, -c.ll[e] / dl);
+                if (dv < 0) amax = fmin(amax, -c.lu[e] / dv);
+            }
+            const real alpha = fmin(real(1), real(0.995) * warp_min(amax));
+            for (int e = lane; e < E; e += 32) {
+                const real du = alpha * c.usol[e];
+                c.ucur[e] += du; c.tl[e] += du; c.tu[e] -= du;
+                c.ll[e] += alpha * c.rt[e];
+                c.lu[e] += alpha * c.dR[e];
+            }
+            ++it;
+        }
+    }
+    // ---- 3. full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
     for (int e = lane; e < E; e += 32) {
         real un;
-        if (exact) un = c.fx[e] == real(1) ? lb : (c.fx[e] == real(2) ? ub : c.ubar[e] + c.usol[e]);
-        else un = fmin(fmax(c.ucur[e], lb), ub);
+        unsigned char f;
+        if (exact) {
+            f = c.fx[e] == real(1) ? 1 : (c.fx[e] == real(2) ? 2 : 0);
+            un = f == 1 ? lb : (f == 2 ? ub : c.ubar[e] + c.usol[e]);
+        } else {
+            un = fmin(fmax(c.ucur[e], lb), ub);
+            f = status == QMPC_STATUS_OK_ ? (c.tl[e] < c.ll[e] ? 1 : (c.tu[e] < c.lu[e] ? 2 : 0)) : 255;
+        }
+        act[e] = f;
         c.ucur[e] = un;
     }
     for (int e = lane; e < E; e += 32) c.usol[e] = c.ucur[e] - c.ubar[e];
@@ -688,7 +777,7 @@ __global__ void __launch_bounds__(WARPS * 32) qmpc_ipm_kernel(IpmArgs<real> a)
     cost = warp_sum(cost);
     for (int e = lane; e < E; e += 32) c.uit[e] = double(c.ucur[e]);
     if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(c.ucur[lane]);
-    if (lane == 0) { a.cost[ocp] = double(cost); a.status[ocp] = status; a.iters[ocp] = it; }
+    if (lane == 0) { a.cost[ocp] = double(cost); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
 }
 
 }  // namespace qmpc

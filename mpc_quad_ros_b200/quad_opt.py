@@ -21,7 +21,7 @@ R_COST = np.array([0.1, 0.1, 0.1, 0.1])
 
 class quad_optimizer:
     def __init__(self, quad, t_horizon=1, n_nodes=100, gpe=None, batch=None, device=None, precision=64,
-                 ipm_mu_tol=0.0, ipm_max_iter=50, ipm_mu_switch=0.0, refine_max_rounds=0):
+                 ipm_mu_tol=0.0, ipm_max_iter=50, ipm_mu_switch=0.0, refine_max_rounds=0, warm_start_rounds=0):
         self.n_nodes, self.t_horizon, self.gpe = n_nodes, t_horizon, gpe
         self.optimization_dt = self.t_horizon / self.n_nodes
         self.terminal_cost = 1
@@ -43,6 +43,7 @@ class quad_optimizer:
         cfg.precision, cfg.device = precision, (self.device.index or 0)
         cfg.ipm_max_iter, cfg.ipm_mu_tol, cfg.t_horizon = ipm_max_iter, ipm_mu_tol, float(t_horizon)
         cfg.ipm_mu_switch, cfg.refine_max_rounds = ipm_mu_switch, refine_max_rounds   # 0 -> library defaults
+        cfg.warm_start_rounds = warm_start_rounds                                     # 0 -> 3 rounds, <0 -> cold IPM every step
         cfg.quad[:] = list(quad.quad_vector())
         cfg.w_diag[:] = list(np.diag(self.W))
         cfg.we_diag[:] = list(np.diag(self.W_e))
@@ -139,6 +140,15 @@ class quad_optimizer:
         it = torch.empty_like(st)
         _capi.check(_capi.lib().qmpc_get_status(self._h, _capi.ptr(st), _capi.ptr(it), self._s()))
         return st, it
+
+    def solver_rounds(self):
+        """active-set refinement rounds of the last solve (warm-start rounds + rounds after the IPM), [B] int32"""
+        r = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+        _capi.check(_capi.lib().qmpc_get_refine_rounds(self._h, _capi.ptr(r), self._s()))
+        return r
+
+    def reset_warm_start(self):
+        _capi.check(_capi.lib().qmpc_reset_warm_start(self._h, self._s()))
 
     def get_iterate(self):
         x = torch.empty((self.batch, self.n_nodes + 1, 13), dtype=torch.float64, device=self.device)

@@ -22,6 +22,9 @@
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)
 
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+
 namespace emu {
 struct uint3e { unsigned x, y, z; };
 struct WarpState {

@@ -10,7 +10,7 @@ using namespace qmpc;
 template <typename real>
 static int run_solve(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                      const double* alpha, double* xit, double* uit, double* u0, double* cost, int* status,
-                     int* iters, real* Wout)
+                     int* iters, int* rounds, unsigned char* act, real* Wout)
 {
     const int B = o->batch, N = o->n_nodes;
     std::vector<real> W((size_t)B * N * WT), fac((size_t)B * N * FAC);
@@ -22,7 +22,7 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
     IpmArgs<real> ia;
     fill_ipm_args(*o, ia);
     ia.x0 = x0; ia.yref = yref; ia.yref_e = yref_e; ia.xit = xit; ia.uit = uit; ia.W = W.data(); ia.fac = fac.data();
-    ia.u0 = u0; ia.cost = cost; ia.status = status; ia.iters = iters;
+    ia.u0 = u0; ia.cost = cost; ia.status = status; ia.iters = iters; ia.rounds = rounds; ia.act = act;
     constexpr int WARPS = 4;
     emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
                 [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
@@ -32,13 +32,13 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
 
 extern "C" int emu_solve_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                             int* status, int* iters, double* Wout)
+                             int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
 {
-    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, Wout);
+    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout);
 }
 extern "C" int emu_solve_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                             int* status, int* iters, float* Wout)
+                             int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
 {
-    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, Wout);
+    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout);
 }
