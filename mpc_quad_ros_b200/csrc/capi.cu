@@ -44,7 +44,10 @@ int fail(int code, const std::string& msg)
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 
-constexpr int IPM_WARPS = 4;
+#ifndef QMPC_IPM_WARPS
+#define QMPC_IPM_WARPS 1      // one OCP per CTA: a finished warp frees its SM slot at once (IPM iteration counts vary)
+#endif
+constexpr int IPM_WARPS = QMPC_IPM_WARPS;
 constexpr int RGP_WARPS = 4;
 
 }  // namespace

@@ -46,8 +46,13 @@ __device__ __forceinline__ T half_sum(unsigned hmask, T v)
 }
 
 template <typename real> __device__ __forceinline__ real rrsqrt(real x);
+#ifdef QMPC_EMU
 template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return 1.0 / sqrt(x); }
 template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return 1.0f / sqrtf(x); }
+#else
+template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return rsqrt(x); }
+template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return rsqrtf(x); }
+#endif
 
 template <typename real> __device__ __forceinline__ bool rfinite(real x) { return x - x == real(0); }
 

@@ -314,11 +314,8 @@ struct WarpCtx {
                     m[c] += t0 * yo[kk]; m[c + 1] += t1 * yo[kk];
                 }
             }
-            if (j < 14 && (j >> 3) == h) {         // cost diagonal
-                const real dg = j < 4 ? a.Rd[j] + (FIXED ? real(0) : dR[k * 4 + j]) : a.Qd[j - 1];
-#pragma unroll
-                for (int ii = 0; ii < 8; ++ii) if (ii == (j & 7)) m[ii] += dg;
-            }
+            // cost diagonal of this column (added where the diagonal entry is consumed)
+            const real dg = j < 4 ? a.Rd[j] + (FIXED ? real(0) : dR[k * 4 + j]) : (j < 14 ? a.Qd[j - 1] : real(0));
             __syncwarp();                          // hv visible; every read of the old P is done
             real g = 0;
 #pragma unroll
@@ -343,7 +340,7 @@ struct WarpCtx {
                 const bool mefix = FIXED && sel4(fxa, lane) != real(0);
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) {
-                    real v = m[aa];
+                    real v = m[aa] + (aa == lane ? dg : real(0));
                     if (FIXED && (mefix || fxa[aa] != real(0))) v = (aa == lane) ? real(1) : real(0);
                     cs[aa * 4 + lane] = v;
                 }
@@ -396,7 +393,7 @@ struct WarpCtx {
                         if (i >= 4 && i < 14) {
                             real l0, l1, l2, l3;
                             ld2(Ls + i * 4, l0, l1); ld2(Ls + i * 4 + 2, l2, l3);
-                            P[(i - 1) * PS + sj] = m[ii] - (l0 * lj[0] + l1 * lj[1] + l2 * lj[2] + l3 * lj[3]);
+                            P[(i - 1) * PS + sj] = m[ii] + (i == j ? dg : real(0)) - (l0 * lj[0] + l1 * lj[1] + l2 * lj[2] + l3 * lj[3]);
                         }
                     }
                     if (h == 0) {
@@ -620,12 +617,12 @@ struct WarpCtx {
     }
 };
 
-#ifndef QMPC_IPM_MIN_BLOCKS
-#define QMPC_IPM_MIN_BLOCKS 4
+#ifndef QMPC_IPM_MIN_WARPS
+#define QMPC_IPM_MIN_WARPS 16      // resident warps per SM the register allocation is sized for
 #endif
 
 template <typename real, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_BLOCKS) qmpc_ipm_kernel(IpmArgs<real> a)
+__global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_ipm_kernel(IpmArgs<real> a)
 {
     QMPC_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
