@@ -299,3 +299,42 @@ def test_fp32_solver_runs_and_is_close():
     assert np.isfinite(u).all() and ((u >= 0) & (u <= 1)).all()
     print(f"fp32: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} status={np.bincount(st)}")
     assert u_rel(u, uo) < 5e-2
+
+
+@pytest.mark.parametrize("M", [20, 50])
+def test_shared_swarm_rgp_vs_sequential_oracle(M):
+    """shared-swarm mode (BASELINE config 3): information-form accumulate + apply on the GPU equals the oracle's
+    sequential single-sample regress over all vehicles (order independent), within the RGP tolerance."""
+    from mpc_quad_ros_b200.swarm import SharedSwarmRGP
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    B, N = 96, 10
+    gp = make_gp(M)
+    gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=1)
+    quad = Quadrotor3D(drag=True, batch=B).set_hummingbird_params()
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe)
+    swarm = SharedSwarmRGP(gpe, opt)
+    rng = np.random.default_rng(5)
+    mu = np.zeros((3, M)); Cm = np.stack([orc.rgp_prior(gp.X[d], gp.theta[d])[0] for d in range(3)])
+    for rnd in range(3):
+        xt = rng.uniform(-9, 9, (B, 3)); yt = -0.3 * xt + 0.02 * rng.standard_normal((B, 3))
+        swarm.update(torch.as_tensor(xt).cuda(), torch.as_tensor(yt).cuda())
+        for v in range(B):
+            for d in range(3):
+                orc.rgp_regress(gp.X[d], gp.theta[d], gp.Kx_inv[d], mu[d], Cm[d], xt[v, d], yt[v, d])
+        assert rel_err(gpe.mu_tensor()[0].cpu().numpy(), mu) < 1e-8
+        assert rel_err(gpe.C_tensor()[0].cpu().numpy(), Cm) < 1e-8
+    # the shared model feeds every vehicle's OCP (alpha broadcast): one fused step runs and matches per-vehicle alpha
+    sc = random_ocp_batch(B, N, 1.0 / N, orc.quad_hummingbird(), gp, seed=9)
+    alpha = gp.alpha(mu)
+    x_ref = torch.as_tensor(sc["yref"][:, :, :13].copy()).cuda()
+    xpp = torch.zeros((B, 13), dtype=torch.float64, device="cuda")
+    u0 = torch.empty((B, 4), dtype=torch.float64, device="cuda")
+    opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
+    opt.step(torch.as_tensor(sc["x0"]).cuda(), x_ref, xpp, True, u0)
+    for b in range(0, B, 17):
+        x, u = sc["xit"][b].copy(), sc["uit"][b].copy()
+        yr, yre = orc.make_yref(sc["yref"][b][:, :13])
+        orc.rti_step(orc.quad_hummingbird(), 1.0 / N, N, sc["x0"][b], yr, yre, x, u, gp=gp, alpha=alpha)
+        assert np.abs(u0[b].cpu().numpy() - u[0]).max() < 1e-6
+    swarm.update()        # residuals left by the fused step
+    assert torch.isfinite(gpe.mu_tensor()).all()
