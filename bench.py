@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cold", action="store_true", help="disable the active-set warm start (cold IPM every step)")
+    ap.add_argument("--warm-rounds", type=int, default=0, help="active-set rounds tried from the previous active set (0 = library default)")
+    ap.add_argument("--mu-switch", type=float, default=0.0, help="IPM -> refinement hand-over complementarity (0 = library default)")
     return ap.parse_args()
 
 
@@ -190,7 +192,7 @@ def b200_arm(a):
         quad = Quadrotor3D(drag=True, batch=B, device=dev).set_hummingbird_params()
         gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B, device=dev) if M else None
         opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision,
-                             warm_start_rounds=(-1 if a.cold else 0))
+                             warm_start_rounds=(-1 if a.cold else a.warm_rounds), ipm_mu_switch=a.mu_switch)
         return ClosedLoop(quad, opt, torch.as_tensor(traj_np), torch.as_tensor(x0_np))
 
     def barrier():
@@ -259,8 +261,11 @@ def b200_arm(a):
     ipm_ms = ms_ipm.value / max(cnt.value, 1)
     ipm_flops = B * n_fact * 12067 * N                # algorithmic flops of the IPM kernel per launch (SURVEY §8d F_ipm per factorisation)
     achieved = ipm_flops / (ipm_ms * 1e-3) / 1e12 if ipm_ms > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this
+    # exact shape (profiles/r01_ipm_summary.txt); other shapes were not captured
+    traffic = 336.1e6 if (B, N, M, a.precision, a.workload, a.cold) == (4096, 20, 20, 64, "random_smooth", False) else None
     roofline = {"kernel": "qmpc_ipm_kernel", "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
-                "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
                 "peak_source": "measured in this run by qmpc_fma_peak (register-resident FMA microbenchmark); "
                                "MEASURED_PEAKS.json has no FMA figure",
                 "ms_per_launch": ipm_ms, "ms_linearize_per_launch": ms_lin.value / max(cnt.value, 1),
@@ -317,9 +322,10 @@ def b200_arm(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle as orc
         nthreads = orc.max_threads()
-        Bs = a.cpu_sample_vehicles or 4 * nthreads
-        v, el, _ = cpu_closed_loop(a, traj_np[:Bs], x0_np[:Bs], 5, nthreads)          # calibrate
-        steps_cpu = int(max(5, min(200, 15.0 * v / Bs)))
+        Bc = min(B, 4 * nthreads)
+        v, el, _ = cpu_closed_loop(a, traj_np[:Bc], x0_np[:Bc], 5, nthreads)          # calibrate
+        steps_cpu = a.warmup + a.steps                                               # same control steps as the GPU run
+        Bs = a.cpu_sample_vehicles or int(max(nthreads, min(B, 15.0 * v / steps_cpu)))  # about 15 s of CPU work
         v, el, it_cpu = cpu_closed_loop(a, traj_np[:Bs], x0_np[:Bs], steps_cpu, nthreads)
         cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": f"first {Bs} vehicles x {steps_cpu} steps of the same workload, {el:.1f} s, C oracle with OpenMP over vehicles "

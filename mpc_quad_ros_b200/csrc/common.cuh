@@ -51,7 +51,7 @@ template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return 
 template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return 1.0f / sqrtf(x); }
 #else
 template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return rsqrt(x); }
-template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return rsqrtf(x); }
+template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return 1.0f / sqrtf(x); }
 #endif
 
 template <typename real> __device__ __forceinline__ bool rfinite(real x) { return x - x == real(0); }
