@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC capi.cu -o libqmpc.so
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -116,7 +117,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     CU_TRY(cudaMemset(h->rounds, 0, B * 4)); CU_TRY(cudaMemset(h->act, 255, B * N * NU));
     if (M) CU_TRY(cudaMemcpy(h->gpX, cfg->gp_X, 3 * M * 8, cudaMemcpyHostToDevice));
     h->x0_src = h->x0; h->alpha_src = h->alpha; h->alpha_stride = 3 * (int)M;
-    const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N) * 8, smem32 = smem64 / 2;
+    const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N) * 8 + 16384, smem32 = smem64 / 2 + 8192;
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
@@ -229,7 +230,9 @@ static int solve_impl(qmpc_solver* h, void* stream)
     ia.x0 = h->x0_src; ia.yref = h->yref; ia.yref_e = h->yref_e; ia.xit = h->xit; ia.uit = h->uit;
     ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
     ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters; ia.rounds = h->rounds; ia.act = h->act;
-    const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real);
+    // QMPC_IPM_SMEM_PAD (bytes per CTA, tuning only): trades resident warps for L1 capacity
+    static const size_t pad = getenv("QMPC_IPM_SMEM_PAD") ? (size_t)atol(getenv("QMPC_IPM_SMEM_PAD")) : 0;
+    const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real) + pad;
     qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
     LAUNCH_CHECK();
     if (e2) CU_TRY(cudaEventRecord(e2, S(stream)));

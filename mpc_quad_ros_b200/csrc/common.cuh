@@ -45,6 +45,16 @@ __device__ __forceinline__ T half_sum(unsigned hmask, T v)
     return v;
 }
 
+// bring one 128-byte line into L1 ahead of use (no-op in the host emulation)
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+#ifndef QMPC_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 template <typename real> __device__ __forceinline__ real rrsqrt(real x);
 #ifdef QMPC_EMU
 template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return 1.0 / sqrt(x); }

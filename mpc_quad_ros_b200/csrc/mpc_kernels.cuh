@@ -246,6 +246,14 @@ struct WarpCtx {
         for (int i = 0; i < NX; ++i) w[i] = __ldg(t + i * 16);
     }
 
+    // L1 prefetch of the tile (13 lines) and factor record (<= 6 lines) of the stage the sweep visits next
+    __device__ __forceinline__ void prefetch_stage(int k, bool with_fac) const
+    {
+        if (k < 0 || k >= N) return;
+        if (lane < NX) prefetch_l1(Wv + (size_t)k * WT + lane * 16);
+        else if (with_fac && lane < NX + 6) prefetch_l1(reinterpret_cast<const char*>(facv + (size_t)k * FAC) + (lane - NX) * 128);
+    }
+
     // Backward Riccati sweep with factorisation.  Gradient: rt (inputs), q column (states), b column (offset).
     // FIXED: inputs flagged in fx are pinned at fv (exact elimination: their rows/columns of M_uu, M_ux become
     // identity/zero and M[:,a] fv_a moves into the gradient); rt = rdel and dR = 0 in that mode.
@@ -267,6 +275,7 @@ struct WarpCtx {
             const real* tile = Wv + (size_t)k * WT;
             real w[NX];
             load_col(k, w);
+            prefetch_stage(k - 1, false);
             const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
             // y = P w: rows r0..r0+6 here, rows o0..o0+6 from the partner lane (row 13 is the zero padding row)
             real ym[7], yo[7];
@@ -440,6 +449,7 @@ struct WarpCtx {
         for (int k = N - 1; k >= 0; --k) {
             real w[NX];
             load_col(k, w);
+            prefetch_stage(k - 1, true);
             const real* f = facv + (size_t)k * FAC;
             Chol4<real> L;
             L.load(f + 56);
@@ -480,6 +490,7 @@ struct WarpCtx {
         for (int k = N - 1; k >= 0; --k) {
             real w[NX];
             load_col(k, w);
+            prefetch_stage(k - 1, false);
             const real* tile = Wv + (size_t)k * WT;
             const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
             real g = 0;
@@ -557,6 +568,7 @@ struct WarpCtx {
             real wr[8];
 #pragma unroll
             for (int c = 0; c < 8; c += 2) ldg2(tr + c, wr[c], wr[c + 1]);
+            prefetch_stage(k + 1, MODE != 2);
             real u[4];
             if (MODE != 2) {
                 const real* f = facv + (size_t)k * FAC;

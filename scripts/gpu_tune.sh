@@ -17,6 +17,7 @@ for lib in $TUNE_LIBS; do
 done
 IFS=';' read -ra EX <<< "$TUNE_EXTRA"
 for extra in "${EX[@]}"; do [ -n "$extra" ] && run $B $extra; done
+for pad in $TUNE_PADS; do export QMPC_IPM_SMEM_PAD=$pad; echo "# pad $pad" >> gpurun_out/tune.log; run $B $TUNE_PAD_ARGS; unset QMPC_IPM_SMEM_PAD; done
 cat gpurun_out/tune.log
 if [ "${NCU:-0}" = "1" ]; then
 STEPS=14 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qmpc_ipm -s 12 -c 1 -f -o gpurun_out/prof_ipm python scripts/profile_step.py > gpurun_out/ncu_ipm.log 2>&1
