@@ -68,6 +68,14 @@ def make_trajectories(a, first_vehicle, count, K):
 
 # ------------------------------------------------------------------------------------------------ CPU legs
 
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU legs override it)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_closed_loop(a, traj, x0, steps, nthreads):
     """the oracle's closed loop (oracle/qmpc_oracle.c, OpenMP over vehicles) on a bounded sample; returns steps/s"""
     from oracle import oracle as orc
@@ -86,9 +94,9 @@ def reference_arm(a):
     if rank != 0:
         return
     from oracle import oracle as orc
-    nthreads = orc.max_threads()
+    nthreads = host_threads()
     # bounded sample of the same workload: first vehicles of the same trajectories, `steps` control steps
-    Bs = a.cpu_sample_vehicles or max(nthreads, 4 * nthreads)
+    Bs = a.cpu_sample_vehicles or min(a.batch, 64 * nthreads)
     K = a.warmup + a.steps + a.nodes + 2
     traj = make_trajectories(a, 0, Bs, K)
     x0 = traj[:, 0, :].copy()
@@ -320,8 +328,7 @@ def b200_arm(a):
     # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        from oracle import oracle as orc
-        nthreads = orc.max_threads()
+        nthreads = host_threads()
         Bc = min(B, 4 * nthreads)
         v, el, _ = cpu_closed_loop(a, traj_np[:Bc], x0_np[:Bc], 5, nthreads)          # calibrate
         steps_cpu = a.warmup + a.steps                                               # same control steps as the GPU run
