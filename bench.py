@@ -44,14 +44,18 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cold", action="store_true", help="disable the active-set warm start (cold IPM every step)")
+    ap.add_argument("--shared-rgp", action="store_true", help="BASELINE config 3: ONE RGP shared by all vehicles on all ranks (NCCL all-reduce per step)")
+    ap.add_argument("--v-peak", type=float, default=15.0, help="lemniscate peak speed (m/s)")
     ap.add_argument("--warm-rounds", type=int, default=0, help="active-set rounds tried from the previous active set (0 = library default)")
     ap.add_argument("--mu-switch", type=float, default=0.0, help="IPM -> refinement hand-over complementarity (0 = library default)")
     return ap.parse_args()
 
 
 def workload_config(a, n_gpus):
-    return {"workload": f"{a.batch} independent quads per GPU, N={a.nodes}, per-vehicle RGP 3x{a.basis} basis points, "
-                        f"{a.workload} references, hummingbird model, closed loop with plant (BASELINE configs[1])",
+    rgp = (f"ONE shared RGP 3x{a.basis} (information-form all-reduce per step, BASELINE configs[2])" if a.shared_rgp
+           else f"per-vehicle RGP 3x{a.basis} basis points (BASELINE configs[1])")
+    return {"workload": f"{a.batch} independent quads per GPU, N={a.nodes}, {rgp}, "
+                        f"{a.workload} references, hummingbird model, closed loop with plant",
             "vehicles_per_gpu": a.batch, "n_nodes": a.nodes, "n_basis": a.basis, "t_horizon": 1.0,
             "references": a.workload, "sharding": f"vehicles x{n_gpus} ranks, no collective",
             "l2": "per-step working set (stage tiles 136 MB + factors 47 MB + RGP covariances 39 MB at the default "
@@ -62,8 +66,9 @@ def make_trajectories(a, first_vehicle, count, K):
     from mpc_quad_ros_b200.trajectory import lemniscate_trajectories, random_smooth_trajectories
     dt = 1.0 / a.nodes
     # per-vehicle Philox stream (seed 1234 + global vehicle index): a rank generates only its own vehicles
-    gen = lemniscate_trajectories if a.workload == "lemniscate" else random_smooth_trajectories
-    return gen(count, K, dt, seed=1234 + first_vehicle)
+    if a.workload == "lemniscate":
+        return lemniscate_trajectories(count, K, dt, v_peak=a.v_peak, seed=1234 + first_vehicle)
+    return random_smooth_trajectories(count, K, dt, seed=1234 + first_vehicle)
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -189,6 +194,7 @@ def b200_arm(a):
     from mpc_quad_ros_b200.gp.GPE import GPEnsemble
     from mpc_quad_ros_b200.quad import Quadrotor3D
     from mpc_quad_ros_b200.quad_opt import quad_optimizer
+    from mpc_quad_ros_b200.swarm import SharedSwarmRGP
     lib = _capi.lib()
 
     B, N, M = a.batch, a.nodes, a.basis
@@ -198,10 +204,11 @@ def b200_arm(a):
 
     def make_loop():
         quad = Quadrotor3D(drag=True, batch=B, device=dev).set_hummingbird_params()
-        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B, device=dev) if M else None
+        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=(1 if a.shared_rgp else B), device=dev) if M else None
         opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision,
                              warm_start_rounds=(-1 if a.cold else a.warm_rounds), ipm_mu_switch=a.mu_switch)
-        return ClosedLoop(quad, opt, torch.as_tensor(traj_np), torch.as_tensor(x0_np))
+        swarm = SharedSwarmRGP(gpe, opt) if (a.shared_rgp and M) else None
+        return ClosedLoop(quad, opt, torch.as_tensor(traj_np), torch.as_tensor(x0_np), shared_swarm=swarm)
 
     def barrier():
         torch.cuda.synchronize()
@@ -302,6 +309,8 @@ def b200_arm(a):
             x_dev.copy_(xs_host[i], non_blocking=True)
             ref_dev.copy_(traj_host[:, i:i + N, :], non_blocking=True)
             lp.opt.step(x_dev, ref_dev, xpp, first_step=(i == 0), u0_out=u_dev)
+            if lp.shared_swarm is not None:
+                lp.shared_swarm.update()
             u_host.copy_(u_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()              # the caller needs u0 on the host every step
 

@@ -53,7 +53,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.mu_switch = real(c.ipm_mu_switch > 0 ? c.ipm_mu_switch : (f64 ? 1e-6 : 1e-4));
     a.refine_gtol = real(f64 ? 1e-12 : 1e-5);
     a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? 10 : c.refine_max_rounds);
-    a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 3 : c.warm_start_rounds);
+    a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
 }
 

@@ -766,6 +766,13 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             ++it;
         }
     }
+    if (status == QMPC_STATUS_NAN_) {
+        // numerical breakdown (e.g. a vehicle that has already crashed): keep the previous iterate, hold its first control
+        for (int e = lane; e < E; e += 32) act[e] = 255;
+        if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(fmin(fmax(c.ubar[lane], lb), ub));
+        if (lane == 0) { a.cost[ocp] = nan(""); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
+        return;
+    }
     // ---- 3. full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
     for (int e = lane; e < E; e += 32) {
         real un;

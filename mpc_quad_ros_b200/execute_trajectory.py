@@ -64,8 +64,9 @@ class ClosedLoop:
          plant period with u0                             (qmpc_plant_period)
     """
 
-    def __init__(self, quad, quad_opt, traj, x_init, simulation_dt=5e-3):
+    def __init__(self, quad, quad_opt, traj, x_init, simulation_dt=5e-3, shared_swarm=None):
         self.quad, self.opt = quad, quad_opt
+        self.shared_swarm = shared_swarm          # swarm.SharedSwarmRGP: one RGP for all vehicles / ranks (config 3)
         self.B, self.N, self.dev = quad_opt.batch, quad_opt.n_nodes, quad_opt.device
         self.traj = traj.to(self.dev, torch.float64).contiguous()
         assert self.traj.shape[0] == self.B and self.traj.shape[2] == 13
@@ -84,6 +85,8 @@ class ClosedLoop:
         lib, s = _capi.lib(), _capi.stream_ptr()
         _capi.check(lib.qmpc_reference_chunk(self.B, self.K, _capi.ptr(self.traj), int(i), self.N, 1, _capi.ptr(self.chunk), s))
         self.opt.step(x_now, self.chunk, self.x_pred_prev, first_step=(i == 0), u0_out=self.u0)
+        if self.shared_swarm is not None:         # accumulate on the GPU -> all-reduce -> identical posterior on every rank
+            self.shared_swarm.update()
         return self.u0
 
     def step(self):
