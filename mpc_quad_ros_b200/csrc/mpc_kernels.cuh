@@ -122,6 +122,7 @@ struct IpmArgs {
     int B, N;
     real Qd[13], QNd[13], Rd[4];   // dt*W_x, W_e, dt*W_u
     real dt, lb, ub, mu_tol;
+    real lam0;                     // initial multipliers of the cold IPM (slacks start at the box centre)
     real mu_switch;                // complementarity at which the IPM hands over to the active-set refinement
     real refine_gtol;              // sign tolerance on the multipliers of pinned inputs
     int max_iter;
@@ -338,29 +339,28 @@ struct WarpCtx {
             real mu4[4];                           // rows 0..3 (inputs) of this lane's column; they live in the h=0 half
 #pragma unroll
             for (int aa = 0; aa < 4; ++aa) mu4[aa] = __shfl_sync(FULL, m[aa], j);
-            real fxa[4] = {0, 0, 0, 0}, fva[4] = {0, 0, 0, 0};
+            // pinned inputs: fva is 0 for free inputs, keep is the 0/1 mask of the free ones
+            real keep[4] = {1, 1, 1, 1}, fva[4] = {0, 0, 0, 0};
             if (FIXED) {
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) { fxa[aa] = fx[k * 4 + aa]; fva[aa] = fv[k * 4 + aa]; }
+                for (int aa = 0; aa < 4; ++aa) { keep[aa] = fx[k * 4 + aa] != real(0) ? real(0) : real(1); fva[aa] = fv[k * 4 + aa]; }
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) g += mu4[aa] * fva[aa];   // M[:,a] fv_a -> gradient
+                for (int aa = 0; aa < 4; ++aa) g = fma(mu4[aa], fva[aa], g);            // M[:,a] fv_a -> gradient
             }
             if (lane < 4) {
-                const bool mefix = FIXED && sel4(fxa, lane) != real(0);
+                const real kme = FIXED ? sel4(keep, lane) : real(1);
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) {
-                    real v = m[aa] + (aa == lane ? dg : real(0));
-                    if (FIXED && (mefix || fxa[aa] != real(0))) v = (aa == lane) ? real(1) : real(0);
-                    cs[aa * 4 + lane] = v;
-                }
+                for (int aa = 0; aa < 4; ++aa) cs[aa * 4 + lane] = FIXED ? m[aa] * (keep[aa] * kme) : m[aa];
 #pragma unroll
                 for (int pi = 0; pi < 3; ++pi) cs[16 + pi * 4 + lane] = ym[pi];    // M[p_i][a] = (P w_a)[p_i]
-                cs[28 + lane] = mefix ? real(0) : g;
+                cs[28 + lane] = g * kme;
+                // diagonal: cost + barrier term; a pinned input keeps an identity row/column
+                cs[lane * 5] = (kme != real(0)) ? cs[lane * 5] + dg : real(1);
             }
             __syncwarp();
             Chol4<real> L;
-            real lg[4], lp[3][4], lj[4];
-            real gpc[3] = {0, 0, 0};               // gradient correction of the position rows from pinned inputs
+            real lg[4], lp[3][4], lj[4], lpme[4];
+            real gpme = 0;                         // gradient correction of "my" position row from pinned inputs
             {
                 real Muu[16];
 #pragma unroll
@@ -375,19 +375,25 @@ struct WarpCtx {
                     ld2(cs + 16 + pi * 4, mpu[0], mpu[1]); ld2(cs + 18 + pi * 4, mpu[2], mpu[3]);
                     if (FIXED) {
 #pragma unroll
-                        for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) { gpc[pi] += mpu[aa] * fva[aa]; mpu[aa] = 0; }
+                        for (int aa = 0; aa < 4; ++aa) mpu[aa] *= keep[aa];
                     }
                     L.fsolve(mpu, lp[pi]);
                 }
+                // the same for "my" position state (lanes 0..2), addressed with the lane index instead of selects
+                real mpu[4];
+                const int pme = lane < 3 ? lane : 2;
+                ld2(cs + 16 + pme * 4, mpu[0], mpu[1]); ld2(cs + 18 + pme * 4, mpu[2], mpu[3]);
+                if (FIXED) {
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) { gpme = fma(mpu[aa], fva[aa], gpme); mpu[aa] *= keep[aa]; }
+                }
+                L.fsolve(mpu, lpme);
             }
             if (FIXED) {
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) if (fxa[aa] != real(0)) mu4[aa] = 0;
+                for (int aa = 0; aa < 4; ++aa) mu4[aa] *= keep[aa];
             }
             L.fsolve(mu4, lj);
-            real lpme[4];                          // l_p of "my" position state (lanes 0..2)
-#pragma unroll
-            for (int aa = 0; aa < 4; ++aa) lpme[aa] = j == 0 ? lp[0][aa] : (j == 1 ? lp[1][aa] : lp[2][aa]);
             if (h == 0) {
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) Ls[j * 4 + aa] = lj[aa];
@@ -402,9 +408,12 @@ struct WarpCtx {
                         if (i >= 4 && i < 14) {
                             real l0, l1, l2, l3;
                             ld2(Ls + i * 4, l0, l1); ld2(Ls + i * 4 + 2, l2, l3);
-                            P[(i - 1) * PS + sj] = m[ii] + (i == j ? dg : real(0)) - (l0 * lj[0] + l1 * lj[1] + l2 * lj[2] + l3 * lj[3]);
+                            real v = fma(-l0, lj[0], m[ii]);
+                            v = fma(-l1, lj[1], v); v = fma(-l2, lj[2], v); v = fma(-l3, lj[3], v);
+                            P[(i - 1) * PS + sj] = v;
                         }
                     }
+                    if ((j >> 3) == h) P[sj * PS + sj] += dg;          // state cost on the diagonal (own write above)
                     if (h == 0) {
 #pragma unroll
                         for (int pi = 0; pi < 3; ++pi) {
@@ -417,9 +426,9 @@ struct WarpCtx {
                 }
                 if (lane < 3) {
 #pragma unroll
-                    for (int pi = 0; pi < 3; ++pi)
-                        P[pi * PS + lane] += ((pi == lane) ? a.Qd[lane] : real(0)) - dot4(lp[pi], lpme);
-                    pv[lane] = hv[lane] + qj + (lane == 0 ? gpc[0] : (lane == 1 ? gpc[1] : gpc[2])) - dot4(lpme, lg);
+                    for (int pi = 0; pi < 3; ++pi) P[pi * PS + lane] -= dot4(lp[pi], lpme);
+                    P[lane * PS + lane] += a.Qd[lane];
+                    pv[lane] = hv[lane] + qj + gpme - dot4(lpme, lg);
                 }
             }
             if (h == 0) {
@@ -684,8 +693,9 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         for (int e = lane; e < E; e += 32) {
             const real u0 = real(0.5) * (lb + ub);
             c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0;     // slacks are carried, never recomputed from u
-            c.ll[e] = 1; c.lu[e] = 1;
+            c.ll[e] = a.lam0; c.lu[e] = a.lam0;
         }
+        real resfac = 1;                  // fraction of the initial stationarity residual still present
         bool refine = a.max_refine > 0;
         real target = refine ? a.mu_switch : a.mu_tol;
         const real inv2E = real(1) / real(2 * E);
@@ -694,7 +704,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
             const real mu = warp_sum(s) * inv2E;
             if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
-            if (mu < target) {
+            if (mu < target && resfac < real(1e-3)) {
                 if (refine) {
                     for (int e = lane; e < E; e += 32)
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
@@ -714,7 +724,8 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             c.template backward_full<false>();
             c.template forward<0>();
             __syncwarp();
-            real amin = 1;
+            // predictor step lengths: primal (slacks) and dual (multipliers) separately
+            real apm = 1, adm = 1;
             for (int e = lane; e < E; e += 32) {
                 const real tl = c.tl[e], tu = c.tu[e];
                 const real du = c.ubar[e] + c.usol[e] - c.ucur[e];
@@ -723,46 +734,55 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
                 c.ua[e] = c.usol[e];
                 c.cl[e] = du * dl; c.cu[e] = -du * dv;
                 c.rt[e] = dl; c.dR[e] = dv;
-                if (du < 0) amin = fmin(amin, -tl / du);
-                if (du > 0) amin = fmin(amin, tu / du);
-                if (dl < 0) amin = fmin(amin, -c.ll[e] / dl);
-                if (dv < 0) amin = fmin(amin, -c.lu[e] / dv);
+                if (du < 0) apm = fmin(apm, -tl / du);
+                if (du > 0) apm = fmin(apm, tu / du);
+                if (dl < 0) adm = fmin(adm, -c.ll[e] / dl);
+                if (dv < 0) adm = fmin(adm, -c.lu[e] / dv);
             }
-            const real aaff = warp_min(amin);
+            const real apa = warp_min(apm), ada = warp_min(adm);
             s = 0;
             for (int e = lane; e < E; e += 32) {
                 const real du = c.ubar[e] + c.ua[e] - c.ucur[e];
-                s += (c.ll[e] + aaff * c.rt[e]) * (c.tl[e] + aaff * du) + (c.lu[e] + aaff * c.dR[e]) * (c.tu[e] - aaff * du);
+                s += (c.ll[e] + ada * c.rt[e]) * (c.tl[e] + apa * du) + (c.lu[e] + ada * c.dR[e]) * (c.tu[e] - apa * du);
             }
             const real muaff = warp_sum(s) * inv2E;
             real sigma = muaff / mu; sigma = sigma * sigma * sigma;
-            const real smu = sigma * mu;
-            // corrector (increment on top of the predictor solution)
-            for (int e = lane; e < E; e += 32)
-                c.rt[e] = -(smu - c.cl[e]) / c.tl[e] + (smu - c.cu[e]) / c.tu[e];
-            __syncwarp();
-            c.backward_vec();
-            c.template forward<1>();
-            __syncwarp();
-            real amax = real(1e30);
-            for (int e = lane; e < E; e += 32) {
-                const real tl = c.tl[e], tu = c.tu[e];
-                const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
-                const real dl = (smu - c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
-                const real dv = (smu - c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
-                c.usol[e] = du; c.rt[e] = dl; c.dR[e] = dv;
-                if (du < 0) amax = fmin(amax, -tl / du);
-                if (du > 0) amax = fmin(amax, tu / du);
-                if (dl < 0) amax = fmin(amax, -c.ll[e] / dl);
-                if (dv < 0) amax = fmin(amax, -c.lu[e] / dv);
+            // corrector (increment on top of the predictor solution).  Safeguard: if the Mehrotra step is blocked
+            // (step length < 1/2) it is recomputed once as a centring step without the second-order term.
+            real so = 1, ap = 1, ad = 1;
+            for (int pass = 0; pass < 2; ++pass) {
+                const real smu = sigma * mu;
+                for (int e = lane; e < E; e += 32)
+                    c.rt[e] = -(smu - so * c.cl[e]) / c.tl[e] + (smu - so * c.cu[e]) / c.tu[e];
+                __syncwarp();
+                c.backward_vec();
+                c.template forward<1>();
+                __syncwarp();
+                real apx = real(1e30), adx = real(1e30);
+                for (int e = lane; e < E; e += 32) {
+                    const real tl = c.tl[e], tu = c.tu[e];
+                    const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
+                    const real dl = (smu - so * c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
+                    const real dv = (smu - so * c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
+                    c.usol[e] = du; c.rt[e] = dl; c.dR[e] = dv;
+                    if (du < 0) apx = fmin(apx, -tl / du);
+                    if (du > 0) apx = fmin(apx, tu / du);
+                    if (dl < 0) adx = fmin(adx, -c.ll[e] / dl);
+                    if (dv < 0) adx = fmin(adx, -c.lu[e] / dv);
+                }
+                ap = warp_min(apx); ad = warp_min(adx);
+                if (pass == 1 || fmin(ap, ad) >= real(0.5)) break;
+                so = 0; sigma = fmax(sigma, real(0.5));
+                __syncwarp();
             }
-            const real alpha = fmin(real(1), real(0.995) * warp_min(amax));
+            ap = fmin(real(1), real(0.995) * ap); ad = fmin(real(1), real(0.995) * ad);
             for (int e = lane; e < E; e += 32) {
-                const real du = alpha * c.usol[e];
+                const real du = ap * c.usol[e];
                 c.ucur[e] += du; c.tl[e] += du; c.tu[e] -= du;
-                c.ll[e] += alpha * c.rt[e];
-                c.lu[e] += alpha * c.dR[e];
+                c.ll[e] += ad * c.rt[e];
+                c.lu[e] += ad * c.dR[e];
             }
+            resfac *= real(1) - fmin(ap, ad);
             ++it;
         }
     }

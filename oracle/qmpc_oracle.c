@@ -389,6 +389,7 @@ static void qp_gradient(const qp_t *qp, const double *us, double *xs, double *gu
     }
 }
 
+int orc_debug = 0;         /* >0: print the IPM iteration log (diagnostic) */
 int orc_last_rounds = 0;   /* refinement rounds of the most recent boxqp_solve (diagnostic, not thread safe) */
 
 /* Mehrotra predictor-corrector on the box-QP, then exact active-set refinement.
@@ -404,64 +405,74 @@ static int boxqp_solve(const qp_t *qp, double *xs, double *us, int *iters_out, d
     double *uc = buf + 6 * n, *dla = buf + 7 * n, *dua = buf + 8 * n, *tl = buf + 9 * n, *tu = buf + 10 * n;
     double *xw = buf + 11 * n;
     double lb = qp->lb, ub = qp->ub;
-    for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); tl[i] = u[i] - lb; tu[i] = ub - u[i]; ll[i] = 1.0; lu[i] = 1.0; }
+    for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); tl[i] = u[i] - lb; tu[i] = ub - u[i]; ll[i] = 0.1; lu[i] = 0.1; }
     int it = 0, status = 2;
-    double mu = 0;
+    double mu = 0, resfac = 1.0;   /* resfac: fraction of the initial stationarity residual still present */
     for (it = 0; it < max_iter; ++it) {
         mu = 0;
         for (int i = 0; i < n; ++i) mu += ll[i] * tl[i] + lu[i] * tu[i];
         mu /= (2.0 * n);
         if (!(mu == mu) || mu > 1e300) { status = 3; break; }
-        if (mu < mu_tol) { status = 1; break; }
+        if (mu < mu_tol && resfac < 1e-3) { status = 1; break; }
         /* predictor */
         for (int i = 0; i < n; ++i) {
             dR[i] = ll[i] / tl[i] + lu[i] / tu[i];
             rt[i] = qp->r[i] - dR[i] * u[i];
         }
         riccati(qp, dR, rt, NULL, NULL, xw, ua);
-        double alpha = 1.0;
+        double ap = 1.0, ad = 1.0;     /* primal (slack) and dual (multiplier) step lengths are separate */
         for (int i = 0; i < n; ++i) {
             double du = ua[i] - u[i];
             dla[i] = -ll[i] - ll[i] / tl[i] * du;
             dua[i] = -lu[i] + lu[i] / tu[i] * du;
-            if (du < 0) alpha = fmin(alpha, -tl[i] / du);
-            if (du > 0) alpha = fmin(alpha, tu[i] / du);
-            if (dla[i] < 0) alpha = fmin(alpha, -ll[i] / dla[i]);
-            if (dua[i] < 0) alpha = fmin(alpha, -lu[i] / dua[i]);
+            if (du < 0) ap = fmin(ap, -tl[i] / du);
+            if (du > 0) ap = fmin(ap, tu[i] / du);
+            if (dla[i] < 0) ad = fmin(ad, -ll[i] / dla[i]);
+            if (dua[i] < 0) ad = fmin(ad, -lu[i] / dua[i]);
         }
         double mua = 0;
         for (int i = 0; i < n; ++i) {
             double du = ua[i] - u[i];
-            mua += (ll[i] + alpha * dla[i]) * (tl[i] + alpha * du) + (lu[i] + alpha * dua[i]) * (tu[i] - alpha * du);
+            mua += (ll[i] + ad * dla[i]) * (tl[i] + ap * du) + (lu[i] + ad * dua[i]) * (tu[i] - ap * du);
         }
         mua /= (2.0 * n);
         double sigma = mua / mu; sigma = sigma * sigma * sigma;
-        /* corrector */
-        for (int i = 0; i < n; ++i) {
-            double du = ua[i] - u[i];
-            double cl = du * dla[i], cu = -du * dua[i];
-            rt[i] = qp->r[i] - dR[i] * u[i] - (sigma * mu - cl) / tl[i] + (sigma * mu - cu) / tu[i];
+        /* corrector; safeguard: a blocked Mehrotra step (< 1/2) is recomputed once as a centring step without the
+           second-order term (Mehrotra's heuristic can otherwise cycle on badly centred iterates) */
+        double so = 1.0;
+        double *cl = uc + 0;   /* uc is re-used below, keep the second-order terms in their own buffers */
+        (void)cl;
+        double *cl2 = (double *)malloc(sizeof(double) * 2 * n), *cu2 = cl2 + n;
+        for (int i = 0; i < n; ++i) { double du = ua[i] - u[i]; cl2[i] = du * dla[i]; cu2[i] = -du * dua[i]; }
+        for (int pass = 0; pass < 2; ++pass) {
+            double smu = sigma * mu;
+            for (int i = 0; i < n; ++i)
+                rt[i] = qp->r[i] - dR[i] * u[i] - (smu - so * cl2[i]) / tl[i] + (smu - so * cu2[i]) / tu[i];
+            riccati(qp, dR, rt, NULL, NULL, xw, uc);
+            ap = 1e300; ad = 1e300;
+            for (int i = 0; i < n; ++i) {
+                double du = uc[i] - u[i];
+                double dl = (smu - so * cl2[i]) / tl[i] - ll[i] - ll[i] / tl[i] * du;
+                double dv = (smu - so * cu2[i]) / tu[i] - lu[i] + lu[i] / tu[i] * du;
+                dla[i] = dl; dua[i] = dv;
+                if (du < 0) ap = fmin(ap, -tl[i] / du);
+                if (du > 0) ap = fmin(ap, tu[i] / du);
+                if (dl < 0) ad = fmin(ad, -ll[i] / dl);
+                if (dv < 0) ad = fmin(ad, -lu[i] / dv);
+            }
+            if (pass == 1 || fmin(ap, ad) >= 0.5) break;
+            so = 0.0; sigma = fmax(sigma, 0.5);
         }
-        riccati(qp, dR, rt, NULL, NULL, xw, uc);
-        double amax = 1e300;
-        for (int i = 0; i < n; ++i) {
-            double dua_ = ua[i] - u[i], du = uc[i] - u[i];
-            double cl = dua_ * dla[i], cu = -dua_ * dua[i];
-            double dl = (sigma * mu - cl) / tl[i] - ll[i] - ll[i] / tl[i] * du;
-            double dv = (sigma * mu - cu) / tu[i] - lu[i] + lu[i] / tu[i] * du;
-            dla[i] = dl; dua[i] = dv;
-            if (du < 0) amax = fmin(amax, -tl[i] / du);
-            if (du > 0) amax = fmin(amax, tu[i] / du);
-            if (dl < 0) amax = fmin(amax, -ll[i] / dl);
-            if (dv < 0) amax = fmin(amax, -lu[i] / dv);
-        }
-        alpha = fmin(1.0, 0.995 * amax);
+        free(cl2);
+        ap = fmin(1.0, 0.995 * ap); ad = fmin(1.0, 0.995 * ad);
+        if (orc_debug) printf("it %2d mu %.3e mu_aff %.3e sigma %.3e alpha %.4f %.4f\n", it, mu, mua, sigma, ap, ad);
         for (int i = 0; i < n; ++i) {
             double du = uc[i] - u[i];
-            u[i] += alpha * du; tl[i] += alpha * du; tu[i] -= alpha * du;
-            ll[i] += alpha * dla[i];
-            lu[i] += alpha * dua[i];
+            u[i] += ap * du; tl[i] += ap * du; tu[i] -= ap * du;
+            ll[i] += ad * dla[i];
+            lu[i] += ad * dua[i];
         }
+        resfac *= 1.0 - fmin(ap, ad);
     }
     double *gu = (double *)malloc(sizeof(double) * n);
     /* IPM answer (clipped into the box: the slacks, not u, carry the sub-ulp distance to a bound) and its KKT residual */

@@ -338,3 +338,29 @@ def test_shared_swarm_rgp_vs_sequential_oracle(M):
         assert np.abs(u0[b].cpu().numpy() - u[0]).max() < 1e-6
     swarm.update()        # residuals left by the fused step
     assert torch.isfinite(gpe.mu_tensor()).all()
+
+
+def test_logger_schema_and_rgp_checkpoint(tmp_path):
+    """log writer with the reference's pickle schema and RGP state checkpoint/restore"""
+    from mpc_quad_ros_b200.Logger import Logger, load_log, load_rgp_state, save_rgp_state
+    from mpc_quad_ros_b200.execute_trajectory import simulate_trajectory
+    from mpc_quad_ros_b200.trajectory import sample_circle_trajectory_accelerating
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    quad = Quadrotor3D(drag=True).set_logged_pysim_params()
+    x0 = np.array([0.0, 0.0, 3.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    quad.set_state(x0)
+    gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [10] * 3, theta=[3.0, 0.1, 0.01])
+    opt = quad_optimizer(quad, t_horizon=1, n_nodes=10, gpe=gpe)
+    nominal = quad_optimizer(quad, t_horizon=1, n_nodes=10)
+    traj, t = sample_circle_trajectory_accelerating(10, 10, 30, 0.1)
+    logger = Logger(str(tmp_path / "run"))
+    simulate_trajectory(quad, opt, nominal, x0, traj, max(t), 6, 5e-3, logger)
+    d = load_log(logger.save_log())
+    for k in ("x_odom", "x_pred_odom", "x_ref", "t_odom", "w_odom", "t_cpu", "cost_solution", "rgp_mu_g_t", "rgp_C_g_t", "v_body", "a_drag"):
+        assert k in d and len(d[k]) == 6, k
+    assert d["x_odom"][0].shape == (13,) and d["w_odom"][0].shape == (4,) and np.stack(d["rgp_C_g_t"][-1]).shape == (3, 10, 10)
+    save_rgp_state(gpe, str(tmp_path / "rgp.npz"))
+    mu = gpe.mu_tensor().clone()
+    gpe.set_state(torch.zeros_like(mu), None)
+    load_rgp_state(gpe, str(tmp_path / "rgp.npz"))
+    assert torch.equal(gpe.mu_tensor(), mu)
