@@ -122,7 +122,7 @@ struct IpmArgs {
     int B, N;
     real Qd[13], QNd[13], Rd[4];   // dt*W_x, W_e, dt*W_u
     real dt, lb, ub, mu_tol;
-    real lam0;                     // initial multipliers of the cold IPM (slacks start at the box centre)
+    real lam0_scale, lam0_min, lam0_max;   // initial multipliers of the cold IPM: clip(scale * mean|dJ/du(centre)|, min, max)
     real mu_switch;                // complementarity at which the IPM hands over to the active-set refinement
     real refine_gtol;              // sign tolerance on the multipliers of pinned inputs
     int max_iter;
@@ -527,6 +527,7 @@ struct WarpCtx {
     // Returns true when the active set is self-consistent: usol then holds the exact minimiser of the box-QP.
     __device__ bool refine_rounds(real lb, real ub, int max_rounds, int& rounds)
     {
+        int prev_changed = 1 << 30;
         for (int round = 0; round < max_rounds; ++round) {
             for (int e = lane; e < E; e += 32) fv[e] = fx[e] == real(1) ? lb - ubar[e] : (fx[e] == real(2) ? ub - ubar[e] : real(0));
             __syncwarp();
@@ -539,13 +540,15 @@ struct WarpCtx {
             int changed = 0;
             for (int e = lane; e < E; e += 32) {
                 const real f = fx[e], un = ubar[e] + usol[e], gr = grad[e];
-                if (f == real(1)) { if (gr < -a.refine_gtol) { fx[e] = 0; changed = 1; } }
-                else if (f == real(2)) { if (gr > a.refine_gtol) { fx[e] = 0; changed = 1; } }
-                else if (un < lb) { fx[e] = 1; changed = 1; }
-                else if (un > ub) { fx[e] = 2; changed = 1; }
+                if (f == real(1)) { if (gr < -a.refine_gtol) { fx[e] = 0; ++changed; } }
+                else if (f == real(2)) { if (gr > a.refine_gtol) { fx[e] = 0; ++changed; } }
+                else if (un < lb) { fx[e] = 1; ++changed; }
+                else if (un > ub) { fx[e] = 2; ++changed; }
             }
-            changed = warp_max(changed);
+            changed = warp_sum(changed);
             if (!changed) return true;
+            if (round >= 2 && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
+            prev_changed = changed;
         }
         return false;
     }
@@ -690,10 +693,23 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     }
     // ---- 2. Mehrotra predictor-corrector IPM (cold start), handing over to the active-set refinement at mu_switch
     if (!exact) {
+        // initial multipliers scaled with the problem: lam0 = clip(0.01 * mean |dJ/du| at the box centre, 0.1, 100)
+        // (one open-loop roll-out + one adjoint sweep; heavily saturated problems otherwise spend many iterations
+        //  growing the multipliers)
+        for (int e = lane; e < E; e += 32) { c.fx[e] = 1; c.fv[e] = real(0.5) * (lb + ub) - c.ubar[e]; }
+        __syncwarp();
+        c.template forward<0, true>();
+        __syncwarp();
+        c.backward_adjoint();
+        __syncwarp();
+        real gs = 0;
+        for (int e = lane; e < E; e += 32) gs += fabs(c.grad[e]);
+        gs = warp_sum(gs) / real(E);
+        const real lam0 = rfinite(gs) ? fmin(fmax(a.lam0_scale * gs, a.lam0_min), a.lam0_max) : a.lam0_min;
         for (int e = lane; e < E; e += 32) {
             const real u0 = real(0.5) * (lb + ub);
             c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0;     // slacks are carried, never recomputed from u
-            c.ll[e] = a.lam0; c.lu[e] = a.lam0;
+            c.ll[e] = lam0; c.lu[e] = lam0;
         }
         real resfac = 1;                  // fraction of the initial stationarity residual still present
         bool refine = a.max_refine > 0;

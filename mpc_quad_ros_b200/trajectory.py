@@ -33,9 +33,9 @@ def sample_circle_trajectory_accelerating(radius, v_max, t_max=10, dt=0.01, star
     return _to_state(p, v), ts
 
 
-def random_smooth_trajectories(B, K, dt, seed=1234, v_max=10.0, z0=3.0):
+def random_smooth_trajectories(B, K, dt, seed=1234, v_max=10.0, z0=3.0, a_max=None):
     """BASELINE config 2: per axis a sum of 3 sinusoids, amplitudes U(1,5) m, frequencies
-    U(0.05,0.3) Hz, random phases, z offset, analytic velocity, scaled so that |v| <= v_max.  Vehicle b uses the
+    U(0.05,0.3) Hz, random phases, z offset, analytic velocity, scaled so that |v| <= v_max (and, if given, |a| <= a_max).  Vehicle b uses the
     counter-based stream seed+b (identical on every rank / in the CPU baseline).  returns [B,K,13]"""
     t = np.arange(K) * dt
     out = np.empty((B, K, 13))
@@ -46,6 +46,9 @@ def random_smooth_trajectories(B, K, dt, seed=1234, v_max=10.0, z0=3.0):
         p = (amp[:, :, None] * np.sin(arg)).sum(1)
         v = (amp[:, :, None] * 2 * np.pi * f[:, :, None] * np.cos(arg)).sum(1)
         s = min(1.0, v_max / max(np.linalg.norm(v, axis=0).max(), 1e-9))
+        if a_max is not None:
+            acc = -(amp[:, :, None] * (2 * np.pi * f[:, :, None]) ** 2 * np.sin(arg)).sum(1)
+            s = min(s, a_max / max(np.linalg.norm(acc, axis=0).max(), 1e-9))
         p, v = p * s, v * s
         p = p - p[:, :1]                      # start at the origin of the pattern ...
         p[2] += z0                            # ... hovering at z0

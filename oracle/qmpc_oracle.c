@@ -405,7 +405,19 @@ static int boxqp_solve(const qp_t *qp, double *xs, double *us, int *iters_out, d
     double *uc = buf + 6 * n, *dla = buf + 7 * n, *dua = buf + 8 * n, *tl = buf + 9 * n, *tu = buf + 10 * n;
     double *xw = buf + 11 * n;
     double lb = qp->lb, ub = qp->ub;
-    for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); tl[i] = u[i] - lb; tu[i] = ub - u[i]; ll[i] = 0.1; lu[i] = 0.1; }
+    /* initial multipliers scaled with the problem: clip(0.01 * mean |dJ/du| at the box centre, 0.1, 100) */
+    double lam0 = 0.1;
+    {
+        double *g0 = (double *)malloc(sizeof(double) * n);
+        for (int i = 0; i < n; ++i) u[i] = 0.5 * (lb + ub);
+        qp_gradient(qp, u, xw, g0);
+        double gs = 0;
+        for (int i = 0; i < n; ++i) gs += fabs(g0[i]);
+        gs /= n;
+        if (gs == gs) lam0 = fmin(fmax(0.01 * gs, 0.1), 100.0);
+        free(g0);
+    }
+    for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); tl[i] = u[i] - lb; tu[i] = ub - u[i]; ll[i] = lam0; lu[i] = lam0; }
     int it = 0, status = 2;
     double mu = 0, resfac = 1.0;   /* resfac: fraction of the initial stationarity residual still present */
     for (it = 0; it < max_iter; ++it) {

