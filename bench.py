@@ -24,6 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per vehicle-group stream
 
 METRIC = "closed_loop_rti_mpc_rgp_control_steps_per_sec"
 UNIT = "control_steps/s"
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cold", action="store_true", help="disable the active-set warm start (cold IPM every step)")
+    ap.add_argument("--groups", type=int, default=8, help="independent vehicle groups per GPU, one CUDA stream each (value leg)")
     ap.add_argument("--shared-rgp", action="store_true", help="BASELINE config 3: ONE RGP shared by all vehicles on all ranks (NCCL all-reduce per step)")
     ap.add_argument("--v-peak", type=float, default=15.0, help="lemniscate peak speed (m/s)")
     ap.add_argument("--warm-rounds", type=int, default=0, help="active-set rounds tried from the previous active set (0 = library default)")
@@ -58,6 +60,7 @@ def workload_config(a, n_gpus):
                         f"{a.workload} references, hummingbird model, closed loop with plant",
             "vehicles_per_gpu": a.batch, "n_nodes": a.nodes, "n_basis": a.basis, "t_horizon": 1.0,
             "references": a.workload, "sharding": f"vehicles x{n_gpus} ranks, no collective",
+            "groups_per_gpu": a.groups,
             "l2": "per-step working set (stage tiles 136 MB + factors 47 MB + RGP covariances 39 MB at the default "
                   "shape) exceeds the 126 MB L2; no explicit flush"}
 
@@ -190,7 +193,7 @@ def b200_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     from mpc_quad_ros_b200 import _capi
-    from mpc_quad_ros_b200.execute_trajectory import ClosedLoop
+    from mpc_quad_ros_b200.execute_trajectory import ClosedLoop, GroupedClosedLoop
     from mpc_quad_ros_b200.gp.GPE import GPEnsemble
     from mpc_quad_ros_b200.quad import Quadrotor3D
     from mpc_quad_ros_b200.quad_opt import quad_optimizer
@@ -202,13 +205,15 @@ def b200_arm(a):
     traj_np = make_trajectories(a, rank * B, B, K)
     x0_np = traj_np[:, 0, :].copy()
 
-    def make_loop():
-        quad = Quadrotor3D(drag=True, batch=B, device=dev).set_hummingbird_params()
-        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=(1 if a.shared_rgp else B), device=dev) if M else None
+    def make_loop(first=0, count=None):
+        count = B if count is None else count
+        quad = Quadrotor3D(drag=True, batch=count, device=dev).set_hummingbird_params()
+        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=(1 if a.shared_rgp else count), device=dev) if M else None
         opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision,
                              warm_start_rounds=(-1 if a.cold else a.warm_rounds), ipm_mu_switch=a.mu_switch)
         swarm = SharedSwarmRGP(gpe, opt) if (a.shared_rgp and M) else None
-        return ClosedLoop(quad, opt, torch.as_tensor(traj_np), torch.as_tensor(x0_np), shared_swarm=swarm)
+        return ClosedLoop(quad, opt, torch.as_tensor(traj_np[first:first + count]), torch.as_tensor(x0_np[first:first + count]),
+                          shared_swarm=swarm)
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,7 +222,8 @@ def b200_arm(a):
             torch.cuda.synchronize()
 
     # ---------------- value: everything resident, K timed steps
-    loop = make_loop()
+    grouped = a.groups > 1 and not a.shared_rgp
+    loop = GroupedClosedLoop(make_loop, B, a.groups) if grouped else make_loop()
     for _ in range(a.warmup):
         loop.step()
     barrier()
@@ -225,14 +231,19 @@ def b200_arm(a):
     l0 = lib.qmpc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    if grouped:
+        loop.fork()
     for _ in range(a.steps):
         loop.step()
+    if grouped:
+        loop.join()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.qmpc_launch_count() - l0
     clocks = sampler.stop() if sampler else None
-    st, it = loop.opt.solver_status()
+    opts = [lp.opt for lp in loop.loops] if grouped else [loop.opt]
+    st = torch.cat([o.solver_status()[0] for o in opts]); it = torch.cat([o.solver_status()[1] for o in opts])
     n_ipm_last = float(it.double().mean().item())
     bad = int((st != 0).sum().item())
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -297,22 +308,38 @@ def b200_arm(a):
         xs, us = rec.run(a.warmup + a.steps, record=True)          # states a closed loop really visits
         torch.cuda.synchronize()
         xs_host = xs.cpu().pin_memory()
-        traj_host = torch.as_tensor(traj_np).pin_memory()
-        lp = make_loop()
-        x_dev = torch.empty((B, 13), dtype=torch.float64, device=dev)
-        ref_dev = torch.empty((B, N, 13), dtype=torch.float64, device=dev)
+        # the caller's per-step reference buffers [B,N,13], contiguous and pinned (one per replayed step)
+        S = a.warmup + a.steps
+        ref_host = torch.empty((S, B, N, 13), dtype=torch.float64).pin_memory()
+        tr = torch.as_tensor(traj_np)
+        for i in range(S):
+            ref_host[i].copy_(tr[:, i:i + N, :])
+        # G independent vehicle groups, one stream each: a group's copies overlap the other groups' kernels
+        G = 1 if a.shared_rgp else a.groups
+        per = B // G
+        streams = [torch.cuda.Stream() for _ in range(G)]
+        grp = []
+        for gi in range(G):
+            with torch.cuda.stream(streams[gi]):
+                grp.append(dict(lp=make_loop(gi * per, per), lo=gi * per, hi=(gi + 1) * per,
+                                x=torch.empty((per, 13), dtype=torch.float64, device=dev),
+                                ref=torch.empty((per, N, 13), dtype=torch.float64, device=dev),
+                                xpp=torch.zeros((per, 13), dtype=torch.float64, device=dev),
+                                u=torch.empty((per, 4), dtype=torch.float64, device=dev)))
+        torch.cuda.synchronize()
         u_host = torch.empty((B, 4), dtype=torch.float64).pin_memory()
-        xpp = torch.zeros((B, 13), dtype=torch.float64, device=dev)
-        u_dev = torch.empty((B, 4), dtype=torch.float64, device=dev)
 
         def e2e_step(i):
-            x_dev.copy_(xs_host[i], non_blocking=True)
-            ref_dev.copy_(traj_host[:, i:i + N, :], non_blocking=True)
-            lp.opt.step(x_dev, ref_dev, xpp, first_step=(i == 0), u0_out=u_dev)
-            if lp.shared_swarm is not None:
-                lp.shared_swarm.update()
-            u_host.copy_(u_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()              # the caller needs u0 on the host every step
+            for st_, g in zip(streams, grp):
+                with torch.cuda.stream(st_):
+                    g["x"].copy_(xs_host[i, g["lo"]:g["hi"]], non_blocking=True)
+                    g["ref"].copy_(ref_host[i, g["lo"]:g["hi"]], non_blocking=True)
+                    g["lp"].opt.step(g["x"], g["ref"], g["xpp"], first_step=(i == 0), u0_out=g["u"])
+                    if g["lp"].shared_swarm is not None:
+                        g["lp"].shared_swarm.update()
+                    u_host[g["lo"]:g["hi"]].copy_(g["u"], non_blocking=True)
+            for st_ in streams:
+                st_.synchronize()                                   # the caller needs every u0 on the host each step
 
         for i in range(a.warmup):
             e2e_step(i)
@@ -332,7 +359,7 @@ def b200_arm(a):
                "h2d_bytes_per_step": B * (13 + N * 13) * 8, "d2h_bytes_per_step": B * 4 * 8,
                "ms_per_step": float(te.item()) / a.steps,
                "note": "per step: pinned-host x_now [B,13] + reference chunk [B,N,13] -> device, quad_optimizer.step, "
-                       "u0 [B,4] -> pinned host, stream sync; states replayed from a recorded closed loop"}
+                       "u0 [B,4] -> pinned host, sync; vehicle groups on separate streams; states replayed from a recorded closed loop"}
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None

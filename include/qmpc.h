@@ -160,6 +160,12 @@ int qrgp_shared_apply(qrgp_handle_t g, const double *info, void *stream);
 int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double *x_now, const double *x_ref,
               double *x_pred_prev, int first_step, double *u0_out, void *stream);
 
+/* the whole closed-loop step in one call: qmpc_reference_chunk(traj, idx) -> qmpc_step -> qmpc_plant_period(x, u0).
+ * traj [B][K][13]; x [B][13] plant state in/out; chunk [B][N][13] and u0 [B][4] caller-owned scratch/outputs. */
+int qmpc_closed_loop_step(qmpc_handle_t h, qrgp_handle_t g, const double *traj, int K, int idx, double *x,
+                          double *x_pred_prev, double *chunk, double *u0, const double *plant /*host[4]*/, double sim_dt,
+                          int n_sub, void *stream);
+
 /* when `g` is a shared model (created with batch == 1) qmpc_step leaves the residual samples of its B vehicles
  * (v_body, a_drag: [B][3] each) in handle-owned buffers for qrgp_shared_accumulate */
 const double *qmpc_residual_x_device(qmpc_handle_t h);

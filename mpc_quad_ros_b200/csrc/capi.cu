@@ -540,6 +540,21 @@ int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const doubl
     return QMPC_OK;
 }
 
+/* One closed-loop control step entirely on `stream` (execute_trajectory.py:196-277 incl. the plant period):
+ * reference chunk at `idx` of traj [B][K][13] -> qmpc_step -> plant advance of x [B][13] with u0. */
+int qmpc_closed_loop_step(qmpc_handle_t h, qrgp_handle_t g, const double* traj, int K, int idx, double* x,
+                          double* x_pred_prev, double* chunk, double* u0, const double* plant, double sim_dt, int n_sub,
+                          void* stream)
+{
+    if (!h || !traj || !x || !x_pred_prev || !chunk || !u0 || !plant) return fail(QMPC_ERR_ARG, "null argument");
+    const int B = h->cfg.batch, N = h->cfg.n_nodes;
+    int rc = qmpc_reference_chunk(B, K, traj, idx, N, 1, chunk, stream);
+    if (rc) return rc;
+    rc = qmpc_step(h, g, x, chunk, x_pred_prev, idx == 0, u0, stream);
+    if (rc) return rc;
+    return qmpc_plant_period(h->cfg.quad, plant, B, x, u0, sim_dt, n_sub, stream);
+}
+
 /* kernel timing for the roofline leg of bench.py: enable, run solves, then read (synchronises the device).
  * ms_lin / ms_ipm = summed device time of the linearize / ipm launches since enabling; count = solves timed. */
 int qmpc_timing_enable(qmpc_handle_t h, int on)

@@ -91,9 +91,15 @@ class ClosedLoop:
 
     def step(self):
         lib, s = _capi.lib(), _capi.stream_ptr()
-        self.control(self.x, self.i)
-        _capi.check(lib.qmpc_plant_period(self._quadv.ctypes.data_as(C.c_void_p), self._plantv.ctypes.data_as(C.c_void_p),
-                                          self.B, _capi.ptr(self.x), _capi.ptr(self.u0), C.c_double(self.sim_dt), self.n_sub, s))
+        if self.shared_swarm is None:        # one C call: chunk -> solve -> u0 -> prediction -> residual -> RGP -> plant
+            g = self.opt.gpe._h if self.opt.gpe is not None else C.c_void_p(0)
+            _capi.check(lib.qmpc_closed_loop_step(self.opt._h, g, _capi.ptr(self.traj), self.K, int(self.i), _capi.ptr(self.x),
+                                                  _capi.ptr(self.x_pred_prev), _capi.ptr(self.chunk), _capi.ptr(self.u0),
+                                                  self._plantv.ctypes.data_as(C.c_void_p), C.c_double(self.sim_dt), self.n_sub, s))
+        else:
+            self.control(self.x, self.i)
+            _capi.check(lib.qmpc_plant_period(self._quadv.ctypes.data_as(C.c_void_p), self._plantv.ctypes.data_as(C.c_void_p),
+                                              self.B, _capi.ptr(self.x), _capi.ptr(self.u0), C.c_double(self.sim_dt), self.n_sub, s))
         self.i += 1
 
     def run(self, steps, record=False):
@@ -106,3 +112,37 @@ class ClosedLoop:
                 us.append(self.u0.clone())
         if record:
             return torch.stack(xs), torch.stack(us)
+
+
+class GroupedClosedLoop:
+    """The same closed loop with the vehicles split into G independent groups, each on its own CUDA stream.
+    Vehicles never interact, so the groups advance independently: the kernels of one group overlap the tail of another
+    (a step's duration is set by its slowest vehicle - IPM iteration counts vary - while most SMs are already idle)."""
+
+    def __init__(self, make_loop, batch, groups):
+        assert batch % groups == 0, "vehicles must split evenly over the groups"
+        self.groups, self.per = groups, batch // groups
+        self.streams = [torch.cuda.Stream() for _ in range(groups)]
+        self.loops = []
+        for g in range(groups):
+            with torch.cuda.stream(self.streams[g]):
+                self.loops.append(make_loop(g * self.per, self.per))
+        torch.cuda.synchronize()
+
+    def step(self):
+        for s, lp in zip(self.streams, self.loops):
+            with torch.cuda.stream(s):
+                lp.step()
+
+    def fork(self):
+        """group streams wait for the work already queued on the current stream"""
+        ev = torch.cuda.Event()
+        ev.record()
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def join(self):
+        """the current stream waits for every group"""
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
