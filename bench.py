@@ -295,7 +295,7 @@ def b200_arm(a):
                 "peak_source": "measured in this run by qmpc_fma_peak (register-resident FMA microbenchmark); "
                                "MEASURED_PEAKS.json has no FMA figure",
                 "ms_per_launch": ipm_ms, "ms_linearize_per_launch": ms_lin.value / max(cnt.value, 1),
-                "share_of_step": ipm_ms / (ms / a.steps) if ms > 0 else None,
+                "share_of_step": ipm_ms / float(lat.mean()) if lat.mean() > 0 else None,   # within the single-stream timing leg
                 "n_ipm_mean": n_ipm_mean, "n_refine_rounds_mean": n_rounds_mean, "n_factorisations_mean": n_fact,
                 "warm_start_success_frac": float(np.mean(n_warm_ok)) if n_warm_ok else None,
                 "algorithmic_flops_per_vehicle_step": flops_per_step(N, M, n_fact),

@@ -364,3 +364,30 @@ def test_logger_schema_and_rgp_checkpoint(tmp_path):
     gpe.set_state(torch.zeros_like(mu), None)
     load_rgp_state(gpe, str(tmp_path / "rgp.npz"))
     assert torch.equal(gpe.mu_tensor(), mu)
+
+
+def test_grouped_streams_equal_single_stream():
+    """GroupedClosedLoop (vehicle groups on separate CUDA streams) is bit-identical to the single-stream loop."""
+    from mpc_quad_ros_b200.execute_trajectory import ClosedLoop, GroupedClosedLoop
+    from mpc_quad_ros_b200.trajectory import random_smooth_trajectories
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    B, N, M, steps = 64, 20, 20, 6
+    traj = random_smooth_trajectories(B, steps + N + 3, 1.0 / N)
+    x0 = traj[:, 0, :].copy()
+
+    def make(first=0, count=B):
+        quad = Quadrotor3D(drag=True, batch=count).set_hummingbird_params()
+        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=count)
+        opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe)
+        return ClosedLoop(quad, opt, torch.as_tensor(traj[first:first + count]), torch.as_tensor(x0[first:first + count]))
+
+    single = make()
+    for _ in range(steps):
+        single.step()
+    grouped = GroupedClosedLoop(make, B, 4)
+    for _ in range(steps):
+        grouped.step()
+    torch.cuda.synchronize()
+    xg = torch.cat([lp.x for lp in grouped.loops]); ug = torch.cat([lp.u0 for lp in grouped.loops])
+    mug = torch.cat([lp.opt.gpe.mu_tensor() for lp in grouped.loops])
+    assert torch.equal(xg, single.x) and torch.equal(ug, single.u0) and torch.equal(mug, single.opt.gpe.mu_tensor())
