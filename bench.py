@@ -289,7 +289,7 @@ def b200_arm(a):
     achieved = ipm_flops / (ipm_ms * 1e-3) / 1e12 if ipm_ms > 0 else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this
     # exact shape (profiles/r01_ipm_summary.txt); other shapes were not captured
-    traffic = 336.1e6 if (B, N, M, a.precision, a.workload, a.cold) == (4096, 20, 20, 64, "random_smooth", False) else None
+    traffic = 341.0e6 if (B, N, M, a.precision, a.workload, a.cold) == (4096, 20, 20, 64, "random_smooth", False) else None
     roofline = {"kernel": "qmpc_ipm_kernel", "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
                 "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
                 "peak_source": "measured in this run by qmpc_fma_peak (register-resident FMA microbenchmark); "
