@@ -222,6 +222,8 @@ def b200_arm(a):
             torch.cuda.synchronize()
 
     # ---------------- value: everything resident, K timed steps
+    if B % max(a.groups, 1) != 0:
+        a.groups = 1
     grouped = a.groups > 1 and not a.shared_rgp
     loop = GroupedClosedLoop(make_loop, B, a.groups) if grouped else make_loop()
     for _ in range(a.warmup):
@@ -301,6 +303,36 @@ def b200_arm(a):
                 "algorithmic_flops_per_vehicle_step": flops_per_step(N, M, n_fact),
                 "whole_step_tflops": value / world * flops_per_step(N, M, n_fact) / 1e12}
 
+    # ---------------- secondary roofline: the HBM-bound RGP update (K3), timed alone with CUDA events
+    roofline_rgp = None
+    if M and not a.shared_rgp:
+        gtest = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B, device=dev)
+        xt = torch.rand((B, 3), dtype=torch.float64, device=dev) * 16 - 8
+        yt = -0.3 * xt
+        for _ in range(3):
+            _capi.check(lib.qrgp_regress(gtest._h, _capi.ptr(xt), _capi.ptr(yt), _capi.stream_ptr()))
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        r0.record()
+        for _ in range(reps):
+            _capi.check(lib.qrgp_regress(gtest._h, _capi.ptr(xt), _capi.ptr(yt), _capi.stream_ptr()))
+        r1.record()
+        torch.cuda.synchronize()
+        rgp_ms = r0.elapsed_time(r1) / reps
+        rgp_bytes = B * 3 * 16 * M * M                 # C read + written once per (vehicle, axis): 16 M^2 bytes
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        peak_gbs = hbm_peak if hbm_peak else 6650.0
+        ach = rgp_bytes / (rgp_ms * 1e-3) / 1e9
+        roofline_rgp = {"kernel": "qrgp_regress_kernel", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": ach / peak_gbs, "traffic": None, "ms_per_launch": rgp_ms,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6650 GB/s (B200_PROFILING.md)",
+                        "note": "covariances of 4096 vehicles (39 MB) fit the 126 MB L2 when launched back to back"}
+        del gtest
+
     # ---------------- e2e: host buffers in, host buffers out, through the Python API (pinned memory)
     e2e = None
     if not a.no_e2e:
@@ -378,7 +410,7 @@ def b200_arm(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f%d" % a.precision, "data": "synthetic", "config": workload_config(a, world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_rgp": roofline_rgp, "cpu_baseline": cpu,
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
                 "solver": {"status_not_ok_last_step": bad, "ipm_iters_mean": n_ipm_mean, "refine_rounds_mean": n_rounds_mean,
                            "warm_start": (not a.cold)}}

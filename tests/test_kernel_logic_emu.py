@@ -39,3 +39,41 @@ def test_emulated_solve_fp32_within_1e4():
     xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, None)
     assert (r["status"] != 2).all()
     assert u_rel(ue, uo) < 2e-2     # fp32 IPM without active-set polish: logic check only (see DESIGN.md, fp32 status)
+
+
+@pytest.mark.parametrize("N,M", [(1, 0), (2, 3), (3, 20)])
+def test_emulated_solve_tiny_horizons(N, M):
+    B, dt = 2, 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(M) if M else None
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=N)
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, None if gp is None else gp.X,
+                                None if gp is None else gp.theta)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue)
+    xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, gp)
+    assert (r["status"] == 0).all() and u_rel(ue, uo) < 1e-9 and x_rel(xe, xo) < 1e-9
+
+
+def test_emulated_warm_start_from_previous_active_set():
+    """second RTI step from the first step's iterate and active set: the warm-started active-set rounds (or the IPM
+    fall-back) must land on the exact minimiser again, and the returned active set is consistent with the controls"""
+    B, N = 2, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(20)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=3, amp_choices=(8.0, 2.0))
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue)
+    act = r1["act"]
+    assert (act <= 2).all()
+    assert ((ue.reshape(B, -1) == 0.0) == (act == 1)).all() and ((ue.reshape(B, -1) == 1.0) == (act == 2)).all()
+    sc2 = dict(sc)
+    sc2["x0"] = sc["x0"] + 0.002 * np.random.default_rng(1).standard_normal(sc["x0"].shape)
+    sc2["xit"], sc2["uit"] = xe.copy(), ue.copy()
+    xo, uo, _, _ = oracle_solve_batch(sc2, quad, dt, N, gp)
+    x2, u2 = xe.copy(), ue.copy()
+    r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=act.copy())
+    assert (r2["status"] == 0).all() and (r2["rounds"] >= 1).all()
+    assert u_rel(u2, uo) < 1e-9 and x_rel(x2, xo) < 1e-9
