@@ -61,7 +61,7 @@ __device__ __forceinline__ void gp_group_eval(const ModelParams<real>& mp, unsig
 }
 
 template <typename real>
-__global__ void __launch_bounds__(128) qmpc_linearize_kernel(LinArgs<real> a)
+__global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real> a)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int node = gt >> 4, j = gt & 15;
