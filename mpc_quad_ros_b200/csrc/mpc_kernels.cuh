@@ -802,6 +802,15 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             ++it;
         }
     }
+    {   // a solve that ended with a non-finite control is a breakdown too (never hand NaN to the plant or the RGP)
+        real chk = 0;
+        for (int e = lane; e < E; e += 32) {
+            const real un = exact ? c.usol[e] : c.ucur[e];
+            chk += un - un;
+        }
+        chk = warp_sum(chk);
+        if (!(chk == real(0))) status = QMPC_STATUS_NAN_;
+    }
     if (status == QMPC_STATUS_NAN_) {
         // numerical breakdown (e.g. a vehicle that has already crashed): keep the previous iterate, hold its first control
         for (int e = lane; e < E; e += 32) act[e] = 255;

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(WARPS * 32) qrgp_regress_kernel(RgpArgs a)
     double* mu = a.mu + (size_t)model * M;
     double* Cm = a.C + (size_t)model * M * M;
     const double xt = a.xt[model], yt = a.yt[model];
-    if (xt != xt) return;                                  // NaN sample = "no update for this axis" (single-axis RGP.regress)
+    if (!(xt - xt == 0.0) || !(yt - yt == 0.0)) return;    // non-finite sample = "no update for this axis" (single-axis RGP.regress; a crashed vehicle)
 
     for (int i = lane; i < M; i += 32) kv[i] = rbf_k(xt, X[i], iL2, sf2);
     __syncwarp();
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(WARPS * 32) qrgp_shared_accumulate_kernel(RgpS
     const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
     for (int v = gw; v < a.B; v += nw) {
         const double xt = a.xt[(size_t)v * 3 + d], yt = a.yt[(size_t)v * 3 + d];
+        if (!(xt - xt == 0.0) || !(yt - yt == 0.0)) continue;   // a vehicle with a non-finite residual must not poison the shared model
         __syncwarp();
         for (int i = lane; i < M; i += 32) kv[i] = rbf_k(xt, X[i], iL2, sf2);
         __syncwarp();
