@@ -362,8 +362,14 @@ def b200_arm(a):
         torch.cuda.synchronize()
         u_host = torch.empty((B, 4), dtype=torch.float64).pin_memory()
 
+        done = [None] * G      # per group: event recorded after the D2H copy of its previous step
+
         def e2e_step(i):
-            for st_, g in zip(streams, grp):
+            # every group is its own closed loop: the host waits for THAT group's u0 of the previous step, then feeds
+            # its next state/reference (pinned host -> device), runs the control step and reads u0 back
+            for gi, (st_, g) in enumerate(zip(streams, grp)):
+                if done[gi] is not None:
+                    done[gi].synchronize()
                 with torch.cuda.stream(st_):
                     g["x"].copy_(xs_host[i, g["lo"]:g["hi"]], non_blocking=True)
                     g["ref"].copy_(ref_host[i, g["lo"]:g["hi"]], non_blocking=True)
@@ -371,17 +377,24 @@ def b200_arm(a):
                     if g["lp"].shared_swarm is not None:
                         g["lp"].shared_swarm.update()
                     u_host[g["lo"]:g["hi"]].copy_(g["u"], non_blocking=True)
-            for st_ in streams:
-                st_.synchronize()                                   # the caller needs every u0 on the host each step
+                    done[gi] = torch.cuda.Event()
+                    done[gi].record(st_)
+
+        def e2e_drain():
+            for ev in done:
+                if ev is not None:
+                    ev.synchronize()
 
         for i in range(a.warmup):
             e2e_step(i)
+        e2e_drain()
         barrier()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for i in range(a.warmup, a.warmup + a.steps):
             e2e_step(i)
+        e2e_drain()                                                 # every u0 of the last step is on the host
         g1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -392,7 +405,8 @@ def b200_arm(a):
                "h2d_bytes_per_step": B * (13 + N * 13) * 8, "d2h_bytes_per_step": B * 4 * 8,
                "ms_per_step": float(te.item()) / a.steps,
                "note": "per step: pinned-host x_now [B,13] + reference chunk [B,N,13] -> device, quad_optimizer.step, "
-                       "u0 [B,4] -> pinned host, sync; vehicle groups on separate streams; states replayed from a recorded closed loop"}
+                       "u0 [B,4] -> pinned host; each vehicle group (own stream) waits for its own u0 before its next step; "
+                       "states replayed from a recorded closed loop"}
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
