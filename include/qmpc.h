@@ -175,6 +175,10 @@ const double *qmpc_residual_y_device(qmpc_handle_t h);
 /* cudaEvents around the two kernels of qmpc_solve: enable, run solves, read summed device times (synchronises). */
 int qmpc_timing_enable(qmpc_handle_t h, int on);
 int qmpc_timing_read(qmpc_handle_t h, double *ms_linearize, double *ms_ipm, int *count);
+/* per-vehicle timeline of the solver kernel: when enabled, every OCP records %globaltimer (ns) when its warp starts
+ * and when it has written its result; read copies [batch][2] (start, end) of the LAST solve to the host (synchronises). */
+int qmpc_timeline_enable(qmpc_handle_t h, int on);
+int qmpc_timeline_read(qmpc_handle_t h, long long *start_end_host);
 /* register-resident FMA microbenchmark: measured non-tensor FMA peak (TFLOP/s); precision 64 or 32; synchronises */
 int qmpc_fma_peak(int precision, double *tflops, void *stream);
 

@@ -1,5 +1,6 @@
 // capi.cu — C-ABI of libqmpc.so (include/qmpc.h): handle management and kernel launches.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC capi.cu -o libqmpc.so
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,8 @@
 #include "aux_kernels.cuh"
 #include "host_params.h"
 #include "mpc_kernels.cuh"
+#include "mpc_kernels_v2.cuh"
+#include "mpc_kernels_dense.cuh"
 #include "rgp_kernels.cuh"
 
 using namespace qmpc;
@@ -49,6 +52,10 @@ inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 #define QMPC_IPM_WARPS 1      // one OCP per CTA: a finished warp frees its SM slot at once (IPM iteration counts vary)
 #endif
 constexpr int IPM_WARPS = QMPC_IPM_WARPS;
+#ifndef QMPC_IPM2_WARPS
+#define QMPC_IPM2_WARPS 2     // two-OCPs-per-warp kernel: 4 OCPs per CTA, 7 CTAs per SM (shared-memory bound)
+#endif
+constexpr int IPM2_WARPS = QMPC_IPM2_WARPS;
 constexpr int RGP_WARPS = 4;
 
 }  // namespace
@@ -62,6 +69,11 @@ struct qmpc_solver {
     int *status = nullptr, *iters = nullptr, *rounds = nullptr;
     unsigned char* act = nullptr;     // [B][4N] active sets remembered for the warm start
     void *W = nullptr, *fac = nullptr;
+    void *xtr = nullptr, *ws = nullptr;   // scratch of the two-OCPs-per-warp solver
+    int* hard = nullptr;              // [B + 1] list of OCPs handed from the screening kernel to the dense kernel, then the count
+    int dense_grid = 0;
+    long long* timeline = nullptr;    // [B][2] per-OCP start/end stamps when enabled
+    int variant = 0;                  // 0: one OCP per warp, 1: two OCPs per warp (QMPC_IPM_VARIANT, tuning/A-B knob)
     const double* x0_src = nullptr;   // where the next solve reads x0 / alpha from (own buffers or bound ones)
     const double* alpha_src = nullptr;
     int alpha_stride = 0;
@@ -108,6 +120,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     ALLOC(h->xt, B * 3 * 8); ALLOC(h->yt, B * 3 * 8); ALLOC(h->rounds, B * 4); ALLOC(h->act, B * N * NU);
     ALLOC(h->W, B * N * WT * h->rsz); ALLOC(h->fac, B * N * FAC * h->rsz);
     ALLOC(h->gpX, 3 * (M ? M : 1) * 8);
+    ALLOC(h->xtr, B * (N + 1) * NX * h->rsz); ALLOC(h->ws, B * 5 * N * NU * h->rsz);
 #undef ALLOC
     CU_TRY(cudaMemset(h->x0, 0, B * NX * 8)); CU_TRY(cudaMemset(h->yref, 0, B * N * NY * 8));
     CU_TRY(cudaMemset(h->yref_e, 0, B * NX * 8)); CU_TRY(cudaMemset(h->alpha, 0, B * 3 * (M ? M : 1) * 8));
@@ -121,6 +134,28 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+    h->variant = getenv("QMPC_IPM_VARIANT") ? atoi(getenv("QMPC_IPM_VARIANT")) : 0;
+    const size_t smem2 = (size_t)2 * IPM2_WARPS * ipm2_smem_reals((int)N) * 8;
+    if (h->variant == 1 && smem2 > 220 * 1024) h->variant = 0;
+    if (h->variant == 1) {
+        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<double, IPM2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<float, IPM2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2 / 2));
+        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<double, IPM2_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<float, IPM2_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    if (h->variant == 2 && N > DN_MAX_N) h->variant = 0;
+    if (h->variant == 2) {
+        const int smemd = dense_layout((int)N).total * 8;
+        CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->hard), (B + 1) * sizeof(int)));
+        CU_TRY(cudaMemset(h->hard, 0, (B + 1) * sizeof(int)));
+        CU_TRY(cudaFuncSetAttribute(qmpc_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
+        CU_TRY(cudaFuncSetAttribute(qmpc_dense_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd / 2));
+        int per_sm = 0, sms = 0;
+        if (h->cfg.precision == 64) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<double>, DN_THREADS, smemd));
+        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<float>, DN_THREADS, smemd / 2));
+        CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        h->dense_grid = (int)std::min<size_t>(B, (size_t)std::max(1, per_sm) * sms);
+    }
     CU_TRY(cudaDeviceSynchronize());
     *out = h;
     return QMPC_OK;
@@ -131,7 +166,7 @@ int qmpc_destroy(qmpc_handle_t h)
     if (!h) return QMPC_OK;
     cudaSetDevice(h->cfg.device);
     void* ps[] = {h->x0, h->yref, h->yref_e, h->alpha, h->xit, h->uit, h->u0, h->cost, h->status, h->iters,
-                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act};
+                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act, h->xtr, h->ws, h->timeline, h->hard};
     for (void* p : ps) if (p) cudaFree(p);
     delete h;
     return QMPC_OK;
@@ -230,10 +265,29 @@ static int solve_impl(qmpc_solver* h, void* stream)
     ia.x0 = h->x0_src; ia.yref = h->yref; ia.yref_e = h->yref_e; ia.xit = h->xit; ia.uit = h->uit;
     ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
     ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters; ia.rounds = h->rounds; ia.act = h->act;
+    ia.timeline = h->timeline;
     // QMPC_IPM_SMEM_PAD (bytes per CTA, tuning only): trades resident warps for L1 capacity
     static const size_t pad = getenv("QMPC_IPM_SMEM_PAD") ? (size_t)atol(getenv("QMPC_IPM_SMEM_PAD")) : 0;
     const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real) + pad;
-    qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
+    if (h->variant == 1) {
+        Ipm2Args<real> i2;
+        i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N);
+        i2.xtr = static_cast<real*>(h->xtr); i2.ws = static_cast<real*>(h->ws);
+        const size_t smem2 = (size_t)2 * IPM2_WARPS * i2.b.smem_per_warp * sizeof(real) + pad;
+        qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
+    } else if (h->variant == 2) {
+        // screening: warm-started active-set rounds in the Riccati kernel; whatever does not settle goes to the dense kernel
+        static const int screen_rounds = getenv("QMPC_SCREEN_ROUNDS") ? atoi(getenv("QMPC_SCREEN_ROUNDS")) : 3;
+        CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
+        ia.hard_list = h->hard; ia.hard_count = h->hard + B;
+        if (ia.warm_rounds > screen_rounds) ia.warm_rounds = screen_rounds;
+        qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
+        LAUNCH_CHECK();
+        DenseArgs<real> dn;
+        dn.b = ia; dn.hard_list = h->hard; dn.hard_count = h->hard + B;
+        qmpc_dense_kernel<real><<<h->dense_grid, DN_THREADS, dense_layout(N).total * sizeof(real), S(stream)>>>(dn);
+    } else
+        qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
     LAUNCH_CHECK();
     if (e2) CU_TRY(cudaEventRecord(e2, S(stream)));
     return QMPC_OK;
@@ -563,6 +617,28 @@ int qmpc_timing_enable(qmpc_handle_t h, int on)
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     h->ev.clear();
     h->timing = on != 0;
+    return QMPC_OK;
+}
+int qmpc_timeline_enable(qmpc_handle_t h, int on)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    CU_TRY(cudaSetDevice(h->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (on && !h->timeline) {
+        CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->timeline), (size_t)h->cfg.batch * 16));
+        CU_TRY(cudaMemset(h->timeline, 0, (size_t)h->cfg.batch * 16));
+    } else if (!on && h->timeline) {
+        cudaFree(h->timeline);
+        h->timeline = nullptr;
+    }
+    return QMPC_OK;
+}
+int qmpc_timeline_read(qmpc_handle_t h, long long* out)
+{
+    if (!h || !out) return fail(QMPC_ERR_ARG, "null argument");
+    if (!h->timeline) return fail(QMPC_ERR_ARG, "timeline not enabled");
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out, h->timeline, (size_t)h->cfg.batch * 16, cudaMemcpyDeviceToHost));
     return QMPC_OK;
 }
 int qmpc_timing_read(qmpc_handle_t h, double* ms_lin, double* ms_ipm, int* count)

@@ -29,6 +29,8 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
 
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
 inline int ipm_smem_reals(int N) { return (SM_VEC + SM_NVEC * 4 * N + (N + 1) * 13 + 9) & ~1; }
+// two-OCPs-per-warp kernel: per-OCP reals, = 8 mod 16 so that the two OCPs of a warp sit half a bank row apart
+inline int ipm2_smem_reals(int N) { int n = 360 + 8 * 4 * N; n += (24 - (n % 16)) % 16; return n; }
 
 template <typename real>
 inline void fill_lin_args(const qmpc_config& c, LinArgs<real>& a)
@@ -56,6 +58,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? 10 : c.refine_max_rounds);
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
+    a.timeline = nullptr; a.hard_list = nullptr; a.hard_count = nullptr;
 }
 
 }  // namespace qmpc

@@ -142,7 +142,21 @@ struct IpmArgs {
     int* status;                   // [B]
     int* iters;                    // [B]  IPM iterations
     int* rounds;                   // [B]  active-set refinement rounds (warm + after the IPM)
+    long long* timeline;           // [B][2] %globaltimer at start / end of each OCP, or null (measurement hook)
+    int* hard_list;                // screening mode (hard_count != null): an OCP whose warm-started rounds do not settle is
+    int* hard_count;               // appended here for the dense kernel instead of running the IPM in this warp
 };
+
+__device__ __forceinline__ long long global_ns()
+{
+#ifdef QMPC_EMU
+    return 0;
+#else
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
 
 template <typename real> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };
@@ -673,6 +687,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     c.xit = a.xit + (size_t)ocp * (N + 1) * NX;
     c.uit = a.uit + (size_t)ocp * N * NU;
     unsigned char* act = a.act + (size_t)ocp * E;
+    if (a.timeline && lane == 0) a.timeline[2 * ocp] = global_ns();
 
     const real lb = a.lb, ub = a.ub;
     for (int e = lane; e < E; e += 32) {
@@ -690,6 +705,10 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         for (int e = lane; e < E; e += 32) { const unsigned char f = act[e]; if (f > 2) known = 0; c.fx[e] = real(f <= 2 ? f : 0); }
         known = -warp_max(-known);
         if (known && c.refine_rounds(lb, ub, a.warm_rounds, rounds)) { exact = true; status = QMPC_STATUS_OK_; }
+    }
+    if (!exact && a.hard_count) {
+        if (lane == 0) a.hard_list[atomicAdd(a.hard_count, 1)] = ocp;
+        return;
     }
     // ---- 2. Mehrotra predictor-corrector IPM (cold start), handing over to the active-set refinement at mu_switch
     if (!exact) {
@@ -816,6 +835,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         for (int e = lane; e < E; e += 32) act[e] = 255;
         if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(fmin(fmax(c.ubar[lane], lb), ub));
         if (lane == 0) { a.cost[ocp] = nan(""); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
+        if (a.timeline && lane == 0) a.timeline[2 * ocp + 1] = global_ns();
         return;
     }
     // ---- 3. full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
@@ -839,6 +859,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     for (int e = lane; e < E; e += 32) c.uit[e] = double(c.ucur[e]);
     if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(c.ucur[lane]);
     if (lane == 0) { a.cost[ocp] = double(cost); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
+    if (a.timeline && lane == 0) a.timeline[2 * ocp + 1] = global_ns();
 }
 
 }  // namespace qmpc

@@ -41,7 +41,7 @@ def make_config(B, N, t_horizon, quad, w_diag, we_diag, gp_X=None, gp_theta=None
     return c, keep
 
 
-def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None):
+def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None, variant=0):
     B, N = cfg.batch, cfg.n_nodes
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     x0, yref, yref_e = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, yref, yref_e))
@@ -50,6 +50,6 @@ def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None):
     status, iters, rounds = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     act = np.full((B, 4 * N), 255, dtype=np.uint8) if act is None else act
     W = np.empty((B, N, 13, 16), dtype=np.float32 if f32 else np.float64)
-    fn = lib().emu_solve_f32 if f32 else lib().emu_solve_f64
+    fn = getattr(lib(), "emu_solve%s_%s" % (("", "2", "3")[variant], "f32" if f32 else "f64"))
     fn(C.byref(cfg), p(x0), p(yref), p(yref_e), p(alpha), p(xit), p(uit), p(u0), p(cost), p(status), p(iters), p(rounds), p(act), p(W))
     return dict(u0=u0, cost=cost, status=status, iters=iters, rounds=rounds, act=act, W=W)

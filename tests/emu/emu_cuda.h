@@ -34,6 +34,7 @@ struct WarpState {
 };
 inline thread_local uint3e t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 inline thread_local WarpState* t_warp;
+inline thread_local std::barrier<>* t_block;
 inline thread_local unsigned char* t_smem;
 inline thread_local int t_lane;
 
@@ -66,11 +67,12 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         unsigned char* sm = smem.data() + ((64 - (reinterpret_cast<uintptr_t>(smem.data()) & 63)) & 63);
         std::vector<std::unique_ptr<WarpState>> warps;
         for (unsigned w = 0; w < block / 32; ++w) warps.emplace_back(new WarpState());
+        std::barrier<> blockbar((std::ptrdiff_t)block);
         std::vector<std::thread> th;
         for (unsigned t = 0; t < block; ++t)
             th.emplace_back([&, t, b]() {
                 t_threadIdx = {t, 0, 0}; t_blockIdx = {b, 0, 0}; t_blockDim = {block, 1, 1}; t_gridDim = {grid, 1, 1};
-                t_warp = warps[t / 32].get(); t_lane = t & 31; t_smem = sm;
+                t_warp = warps[t / 32].get(); t_lane = t & 31; t_smem = sm; t_block = &blockbar;
                 body();
                 // a lane that returned early must still let its warp-mates pass later barriers: kernels in this
                 // repo only exit whole warps / whole 16-lane groups, so nothing to do here.
@@ -89,4 +91,6 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
 template <typename T> inline T __shfl_sync(unsigned m, T v, int src) { return emu::shfl(m, v, src); }
 template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return emu::shfl(m, v, emu::t_lane ^ x); }
 inline void __syncwarp(unsigned m = 0xffffffffu) { emu::sync(m); }
+inline void __syncthreads() { emu::t_block->arrive_and_wait(); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldg(const T* p) { return *p; }

@@ -3,6 +3,8 @@
 #define QMPC_EMU 1
 #include "emu_cuda.h"
 #include "../../mpc_quad_ros_b200/csrc/mpc_kernels.cuh"
+#include "../../mpc_quad_ros_b200/csrc/mpc_kernels_v2.cuh"
+#include "../../mpc_quad_ros_b200/csrc/mpc_kernels_dense.cuh"
 #include "../../mpc_quad_ros_b200/csrc/host_params.h"
 
 using namespace qmpc;
@@ -10,7 +12,7 @@ using namespace qmpc;
 template <typename real>
 static int run_solve(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                      const double* alpha, double* xit, double* uit, double* u0, double* cost, int* status,
-                     int* iters, int* rounds, unsigned char* act, real* Wout)
+                     int* iters, int* rounds, unsigned char* act, real* Wout, int variant = 0)
 {
     const int B = o->batch, N = o->n_nodes;
     std::vector<real> W((size_t)B * N * WT), fac((size_t)B * N * FAC);
@@ -24,8 +26,25 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
     ia.x0 = x0; ia.yref = yref; ia.yref_e = yref_e; ia.xit = xit; ia.uit = uit; ia.W = W.data(); ia.fac = fac.data();
     ia.u0 = u0; ia.cost = cost; ia.status = status; ia.iters = iters; ia.rounds = rounds; ia.act = act;
     constexpr int WARPS = 4;
-    emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
-                [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
+    if (variant == 0) {
+        emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
+                    [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
+    } else if (variant == 2) {      // screening kernel (warm-started rounds) + dense kernel for the rest
+        std::vector<int> list(B), cnt(1, 0);
+        ia.hard_list = list.data(); ia.hard_count = cnt.data();
+        emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
+                    [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
+        DenseArgs<real> dn;
+        dn.b = ia; dn.hard_list = list.data(); dn.hard_count = cnt.data();
+        emu::launch(2, DN_THREADS, (size_t)dense_layout(N).total * sizeof(real), [&]() { qmpc_dense_kernel<real>(dn); });
+    } else {
+        constexpr int W2 = 2;
+        std::vector<real> xtr((size_t)B * (N + 1) * NX), ws((size_t)B * 5 * 4 * N);
+        Ipm2Args<real> i2;
+        i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N); i2.xtr = xtr.data(); i2.ws = ws.data();
+        emu::launch((B + 2 * W2 - 1) / (2 * W2), W2 * 32, (size_t)2 * W2 * i2.b.smem_per_warp * sizeof(real),
+                    [&]() { qmpc_ipm2_kernel<real, W2>(i2); });
+    }
     if (Wout) std::memcpy(Wout, W.data(), W.size() * sizeof(real));
     return 0;
 }
@@ -41,4 +60,29 @@ extern "C" int emu_solve_f32(const HostOcp* o, const double* x0, const double* y
                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
 {
     return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout);
+}
+
+extern "C" int emu_solve2_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
+                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
+                              int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
+{
+    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 1);
+}
+extern "C" int emu_solve3_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
+                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
+                              int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
+{
+    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 2);
+}
+extern "C" int emu_solve3_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
+                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
+                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
+{
+    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 2);
+}
+extern "C" int emu_solve2_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
+                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
+                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
+{
+    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 1);
 }

@@ -9,8 +9,14 @@ from helpers import make_gp, oracle_solve_batch, random_ocp_batch, u_rel, x_rel
 from emu import emu
 
 
+# the dense kernel works on the condensed Hessian (cond ~1e6..1e7): ~1e-9 relative instead of ~1e-12; north_star asks 1e-6
+TOL = {0: 1e-9, 1: 1e-9, 2: 2e-8}
+VARIANTS = pytest.mark.parametrize("variant", [0, 1, 2], ids=["warp_per_ocp", "two_ocps_per_warp", "screen_plus_dense"])
+
+
+@VARIANTS
 @pytest.mark.parametrize("N,use_gp", [(20, True), (10, False), (7, True)])
-def test_emulated_solve_matches_oracle(N, use_gp):
+def test_emulated_solve_matches_oracle(N, use_gp, variant):
     B, dt = 3, 1.0 / N
     quad = orc.quad_hummingbird()
     gp = make_gp() if use_gp else None
@@ -18,7 +24,7 @@ def test_emulated_solve_matches_oracle(N, use_gp):
     cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, None if gp is None else gp.X,
                                 None if gp is None else gp.theta)
     xe, ue = sc["xit"].copy(), sc["uit"].copy()
-    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue)
+    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=variant)
     xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, gp)
     assert (r["status"] == 0).all()
     assert u_rel(ue, uo) < 1e-7                        # fp64 tolerance of north_star: 1e-6
@@ -28,21 +34,23 @@ def test_emulated_solve_matches_oracle(N, use_gp):
     assert np.abs(xe[:, 0] - sc["x0"]).max() == 0.0
 
 
-def test_emulated_solve_fp32_within_1e4():
+@VARIANTS
+def test_emulated_solve_fp32_within_1e4(variant):
     B, N = 2, 10
     dt = 1.0 / N
     quad = orc.quad_hummingbird()
     sc = random_ocp_batch(B, N, dt, quad, None, seed=5, amp_choices=(2.0,))
     cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG)
     xe, ue = sc["xit"].copy(), sc["uit"].copy()
-    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], None, xe, ue, f32=True)
+    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], None, xe, ue, f32=True, variant=variant)
     xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, None)
     assert (r["status"] != 2).all()
     assert u_rel(ue, uo) < 2e-2     # fp32 IPM without active-set polish: logic check only (see DESIGN.md, fp32 status)
 
 
+@VARIANTS
 @pytest.mark.parametrize("N,M", [(1, 0), (2, 3), (3, 20)])
-def test_emulated_solve_tiny_horizons(N, M):
+def test_emulated_solve_tiny_horizons(N, M, variant):
     B, dt = 2, 1.0 / N
     quad = orc.quad_hummingbird()
     gp = make_gp(M) if M else None
@@ -50,22 +58,23 @@ def test_emulated_solve_tiny_horizons(N, M):
     cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, None if gp is None else gp.X,
                                 None if gp is None else gp.theta)
     xe, ue = sc["xit"].copy(), sc["uit"].copy()
-    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue)
+    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=variant)
     xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, gp)
-    assert (r["status"] == 0).all() and u_rel(ue, uo) < 1e-9 and x_rel(xe, xo) < 1e-9
+    assert (r["status"] == 0).all() and u_rel(ue, uo) < TOL[variant] and x_rel(xe, xo) < TOL[variant]
 
 
-def test_emulated_warm_start_from_previous_active_set():
+@VARIANTS
+def test_emulated_warm_start_from_previous_active_set(variant):
     """second RTI step from the first step's iterate and active set: the warm-started active-set rounds (or the IPM
     fall-back) must land on the exact minimiser again, and the returned active set is consistent with the controls"""
-    B, N = 2, 20
+    B, N = 3, 20      # odd batch: the last warp of the two-OCP kernel carries an idle half
     dt = 1.0 / N
     quad = orc.quad_hummingbird()
     gp = make_gp(20)
     sc = random_ocp_batch(B, N, dt, quad, gp, seed=3, amp_choices=(8.0, 2.0))
     cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
     xe, ue = sc["xit"].copy(), sc["uit"].copy()
-    r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue)
+    r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=variant)
     act = r1["act"]
     assert (act <= 2).all()
     assert ((ue.reshape(B, -1) == 0.0) == (act == 1)).all() and ((ue.reshape(B, -1) == 1.0) == (act == 2)).all()
@@ -74,6 +83,6 @@ def test_emulated_warm_start_from_previous_active_set():
     sc2["xit"], sc2["uit"] = xe.copy(), ue.copy()
     xo, uo, _, _ = oracle_solve_batch(sc2, quad, dt, N, gp)
     x2, u2 = xe.copy(), ue.copy()
-    r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=act.copy())
+    r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=act.copy(), variant=variant)
     assert (r2["status"] == 0).all() and (r2["rounds"] >= 1).all()
-    assert u_rel(u2, uo) < 1e-9 and x_rel(x2, xo) < 1e-9
+    assert u_rel(u2, uo) < TOL[variant] and x_rel(x2, xo) < TOL[variant]
