@@ -73,7 +73,8 @@ struct qmpc_solver {
     int* hard = nullptr;              // [B + 1] list of OCPs handed from the screening kernel to the dense kernel, then the count
     int dense_grid = 0;
     long long* timeline = nullptr;    // [B][2] per-OCP start/end stamps when enabled
-    int variant = 0;                  // 0: one OCP per warp, 1: two OCPs per warp (QMPC_IPM_VARIANT, tuning/A-B knob)
+    int variant = 2;                  // QMPC_IPM_VARIANT (A/B knob): 0 Riccati kernel alone (one OCP per warp), 1 two OCPs per warp,
+                                      // 2 (default) Riccati screening + dense kernel, 3 two-OCP screening + dense kernel
     const double* x0_src = nullptr;   // where the next solve reads x0 / alpha from (own buffers or bound ones)
     const double* alpha_src = nullptr;
     int alpha_stride = 0;
@@ -134,17 +135,17 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-    h->variant = getenv("QMPC_IPM_VARIANT") ? atoi(getenv("QMPC_IPM_VARIANT")) : 0;
+    h->variant = getenv("QMPC_IPM_VARIANT") ? atoi(getenv("QMPC_IPM_VARIANT")) : 2;
     const size_t smem2 = (size_t)2 * IPM2_WARPS * ipm2_smem_reals((int)N) * 8;
-    if (h->variant == 1 && smem2 > 220 * 1024) h->variant = 0;
-    if (h->variant == 1) {
+    if ((h->variant == 1 || h->variant == 3) && smem2 > 220 * 1024) h->variant = 0;
+    if (h->variant == 1 || h->variant == 3) {
         CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<double, IPM2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<float, IPM2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2 / 2));
         CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<double, IPM2_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<float, IPM2_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
-    if (h->variant == 2 && N > DN_MAX_N) h->variant = 0;
-    if (h->variant == 2) {
+    if ((h->variant == 2 || h->variant == 3) && N > DN_MAX_N) h->variant -= 2;
+    if (h->variant == 2 || h->variant == 3) {
         const int smemd = dense_layout((int)N).total * 8;
         CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->hard), (B + 1) * sizeof(int)));
         CU_TRY(cudaMemset(h->hard, 0, (B + 1) * sizeof(int)));
@@ -275,13 +276,20 @@ static int solve_impl(qmpc_solver* h, void* stream)
         i2.xtr = static_cast<real*>(h->xtr); i2.ws = static_cast<real*>(h->ws);
         const size_t smem2 = (size_t)2 * IPM2_WARPS * i2.b.smem_per_warp * sizeof(real) + pad;
         qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
-    } else if (h->variant == 2) {
-        // screening: warm-started active-set rounds in the Riccati kernel; whatever does not settle goes to the dense kernel
-        static const int screen_rounds = getenv("QMPC_SCREEN_ROUNDS") ? atoi(getenv("QMPC_SCREEN_ROUNDS")) : 3;
+    } else if (h->variant == 2 || h->variant == 3) {
+        // screening: warm-started active-set rounds in a Riccati kernel; whatever does not settle goes to the dense kernel
+        static const int screen_rounds = getenv("QMPC_SCREEN_ROUNDS") ? atoi(getenv("QMPC_SCREEN_ROUNDS")) : 6;
         CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
         ia.hard_list = h->hard; ia.hard_count = h->hard + B;
         if (ia.warm_rounds > screen_rounds) ia.warm_rounds = screen_rounds;
-        qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
+        if (h->variant == 3) {
+            Ipm2Args<real> i2;
+            i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N);
+            i2.xtr = static_cast<real*>(h->xtr); i2.ws = static_cast<real*>(h->ws);
+            const size_t smem2 = (size_t)2 * IPM2_WARPS * i2.b.smem_per_warp * sizeof(real) + pad;
+            qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
+        } else
+            qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
         LAUNCH_CHECK();
         DenseArgs<real> dn;
         dn.b = ia; dn.hard_list = h->hard; dn.hard_count = h->hard + B;

@@ -177,6 +177,14 @@ __device__ __forceinline__ void ldg2(const real* p, real& a, real& b)
 }
 
 template <typename real>
+__device__ __forceinline__ void st2(real* p, real a, real b)
+{
+    typename Vec2<real>::type v;
+    v.x = a; v.y = b;
+    *reinterpret_cast<typename Vec2<real>::type*>(p) = v;
+}
+
+template <typename real>
 struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal
     real l10, l20, l21, l30, l31, l32, i0, i1, i2, i3;
     __device__ __forceinline__ void factor(const real* M /* 4x4 row-major, lower used */)

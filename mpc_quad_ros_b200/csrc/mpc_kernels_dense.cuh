@@ -15,7 +15,8 @@
 namespace qmpc {
 
 constexpr int DN_THREADS = 256;
-constexpr int DN_MAX_N = 22;        // N(N+1)/2 tiles <= 256 threads and E = 4N <= 96 (three rows per lane in the solves)
+constexpr int DN_MAX_N = 21;        // N(N+1)/2 tiles + N right-hand-side threads <= 256
+constexpr int TS = 18;              // reals per 4x4 tile in shared memory: 144 B stride spreads consecutive tiles over the banks
 
 template <typename real>
 struct DenseArgs {
@@ -26,100 +27,162 @@ struct DenseArgs {
 
 // shared-memory carve-up (reals)
 struct DenseLayout {
-    int E, T, GS, Ht, Lt, G, ev, sml, vec, total;
+    int E, T, GS, Ht, Lt, G, ev, sq, sml, tb, dxs, vec, total;
 };
+constexpr int DN_NVEC = 18;
 __host__ __device__ inline DenseLayout dense_layout(int N)
 {
     DenseLayout L;
     L.E = 4 * N; L.T = N * (N + 1) / 2; L.GS = L.E + 4;
-    L.Ht = 0; L.Lt = L.T * 16; L.G = 2 * L.T * 16; L.ev = L.G + 13 * L.GS; L.sml = L.ev + 16; L.vec = L.sml + 48;
-    L.total = L.vec + 14 * L.E;
+    L.Ht = 0; L.Lt = L.T * TS; L.G = 2 * L.T * TS; L.ev = L.G + 13 * L.GS; L.sq = L.ev + 16; L.sml = L.sq + 32;
+    L.tb = L.sml + 64;                   // small: wv(16) xp(16) reduction scratch(16) control words(16)
+    L.dxs = L.tb + 2 * WT;               // two staged stage tiles
+    L.vec = (L.dxs + 13 * (N + 1) + 1) & ~1;
+    L.total = L.vec + DN_NVEC * L.E;
     return L;
 }
-constexpr int DN_NVEC = 14;
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // tile (i, j), j <= i
+
+// inverse of a 4x4 Cholesky factor (lower triangular, row-major packed): triangular solves become short products
+template <typename real>
+struct Inv4 {
+    real n00, n10, n11, n20, n21, n22, n30, n31, n32, n33;
+    __device__ __forceinline__ void from(const Chol4<real>& L)
+    {
+        n00 = L.i0; n11 = L.i1; n22 = L.i2; n33 = L.i3;
+        n10 = -L.l10 * n00 * n11;
+        n21 = -L.l21 * n11 * n22;
+        n32 = -L.l32 * n22 * n33;
+        n20 = -(L.l20 * n00 + L.l21 * n10) * n22;
+        n31 = -(L.l31 * n11 + L.l32 * n21) * n33;
+        n30 = -(L.l30 * n00 + L.l31 * n10 + L.l32 * n20) * n33;
+    }
+    __device__ __forceinline__ void store(real* p) const
+    {
+        p[0] = n00; p[1] = n10; p[2] = n11; p[3] = n20; p[4] = n21; p[5] = n22; p[6] = n30; p[7] = n31; p[8] = n32; p[9] = n33;
+    }
+    __device__ __forceinline__ void load(const real* p)
+    {
+        ld2(p, n00, n10); ld2(p + 2, n11, n20); ld2(p + 4, n21, n22); ld2(p + 6, n30, n31); ld2(p + 8, n32, n33);
+    }
+    __device__ __forceinline__ void mul(const real* v, real* z) const      // z = Lam^-1 v
+    {
+        z[0] = n00 * v[0];
+        z[1] = n10 * v[0] + n11 * v[1];
+        z[2] = (n20 * v[0] + n21 * v[1]) + n22 * v[2];
+        z[3] = (n30 * v[0] + n31 * v[1]) + (n32 * v[2] + n33 * v[3]);
+    }
+    __device__ __forceinline__ void mulT(const real* v, real* z) const     // z = Lam^-T v
+    {
+        z[0] = (n00 * v[0] + n10 * v[1]) + (n20 * v[2] + n30 * v[3]);
+        z[1] = (n11 * v[1] + n21 * v[2]) + n31 * v[3];
+        z[2] = n22 * v[2] + n32 * v[3];
+        z[3] = n33 * v[3];
+    }
+};
 
 template <typename real>
 struct DenseCtx {
     const IpmArgs<real>& a;
     int tid, lane, N, E, T, GS, ti, tj;
     real *Ht, *Lt, *G, *ev;
-    real *f, *ubar, *ucur, *tl, *tu, *ll, *lu, *cl, *cu, *ua, *usol, *rt, *dR, *tv, *fx, *fv, *grad;
+    real *f, *ubar, *ucur, *tl, *tu, *ll, *lu, *cl, *cu, *ua, *usol, *rt, *dR, *tv, *itl, *itu, *ill, *ilu, *fx, *fv;
 
     // tv = H x  (thread per row; H symmetric, stored as 4x4 tiles of the lower triangle)
     __device__ __forceinline__ void matvec(const real* x)
     {
         if (tid < E) {
             const int I = tid >> 2, ar = tid & 3;
-            real s0 = 0, s1 = 0;
+            real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
             for (int J = 0; J <= I; ++J) {
-                const real* p = Ht + tri(I, J) * 16 + ar * 4;
+                const real* p = Ht + tri(I, J) * TS + ar * 4;
                 real h0, h1, h2, h3, x0, x1, x2, x3;
                 ld2(p, h0, h1); ld2(p + 2, h2, h3);
                 ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
-                s0 += h0 * x0 + h2 * x2; s1 += h1 * x1 + h3 * x3;
+                s0 = fma(h0, x0, s0); s1 = fma(h1, x1, s1); s2 = fma(h2, x2, s2); s3 = fma(h3, x3, s3);
             }
             for (int J = I + 1; J < N; ++J) {
-                const real* p = Ht + tri(J, I) * 16 + ar;
+                const real* p = Ht + tri(J, I) * TS + ar;
                 real x0, x1, x2, x3;
                 ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
-                s0 += p[0] * x0 + p[8] * x2; s1 += p[4] * x1 + p[12] * x3;
+                s0 = fma(p[0], x0, s0); s1 = fma(p[4], x1, s1); s2 = fma(p[8], x2, s2); s3 = fma(p[12], x3, s3);
             }
-            tv[tid] = s0 + s1;
+            tv[tid] = (s0 + s1) + (s2 + s3);
         }
     }
 
     // Lt = chol(K): K = H + diag(dR) (IPM) or H with the inputs flagged in fx replaced by identity rows/columns.
-    // One thread per 4x4 tile; right-looking over block columns, the current panel goes through shared memory.
+    // One thread per 4x4 tile, right-looking over block columns; the current panel goes through shared memory and
+    // the next diagonal block is factored while the other tiles take their update.  Diagonal tiles of Lt hold the
+    // INVERSE of their 4x4 factor.  Threads T..T+N-1 carry the right-hand side rt along as one more block row, so
+    // rt leaves as Lam^-1 rt (the forward substitution costs no extra pass).
     __device__ __forceinline__ void factor(const bool fixed)
     {
         real acc[16];
-        if (tid < T) {
-            const real* p = Ht + tid * 16;
+        real r4[4] = {0, 0, 0, 0};
+        const bool tile = tid < T, rhs = tid >= T && tid < T + N;
+        const int J = tid - T;
+        if (tile) {
+            const real* p = Ht + tid * TS;
 #pragma unroll
             for (int t = 0; t < 16; t += 2) ld2(p + t, acc[t], acc[t + 1]);
-            real ki[4], kj[4];
+            if (fixed) {
+                real ki[4], kj[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ki[q] = (fixed && fx[4 * ti + q] != real(0)) ? real(0) : real(1);
-                kj[q] = (fixed && fx[4 * tj + q] != real(0)) ? real(0) : real(1);
+                for (int q = 0; q < 4; ++q) {
+                    ki[q] = fx[4 * ti + q] != real(0) ? real(0) : real(1);
+                    kj[q] = fx[4 * tj + q] != real(0) ? real(0) : real(1);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[q * 4 + r] *= ki[q] * kj[r];
+                if (ti == tj) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (ki[q] == real(0)) acc[q * 5] = real(1);
+                }
+            } else if (ti == tj) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q * 5] += dR[4 * ti + q];
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) acc[q * 4 + r] *= ki[q] * kj[r];
-            if (ti == tj) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[q * 5] = ki[q] != real(0) ? acc[q * 5] + (fixed ? real(0) : dR[4 * ti + q]) : real(1);
-            }
+        } else if (rhs) {
+            ld2(rt + 4 * J, r4[0], r4[1]); ld2(rt + 4 * J + 2, r4[2], r4[3]);
         }
+        if (tid == 0) {
+            Chol4<real> L;
+            L.factor(acc);
+            Inv4<real> Ni;
+            Ni.from(L);
+            Ni.store(Lt);
+        }
+        __syncthreads();
         for (int K = 0; K < N; ++K) {
-            if (tid < T && ti == K && tj == K) {
-                Chol4<real> L;
-                L.factor(acc);
-                L.store(Lt + tid * 16);
-            }
-            __syncthreads();
-            if (tid < T && tj == K && ti > K) {
-                Chol4<real> L;
-                L.load(Lt + tri(K, K) * 16);
+            if (tile && tj == K && ti > K) {
+                Inv4<real> Ni;
+                Ni.load(Lt + tri(K, K) * TS);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     real z[4];
-                    L.fsolve(acc + q * 4, z);
+                    Ni.mul(acc + q * 4, z);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[q * 4 + r] = z[r];
                 }
-                real* o = Lt + tid * 16;
+                real* o = Lt + tid * TS;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) o[t] = acc[t];
+                for (int t = 0; t < 16; t += 2) st2(o + t, acc[t], acc[t + 1]);
+            } else if (rhs && J == K) {
+                Inv4<real> Ni;
+                Ni.load(Lt + tri(K, K) * TS);
+                real y[4];
+                Ni.mul(r4, y);
+                st2(rt + 4 * K, y[0], y[1]); st2(rt + 4 * K + 2, y[2], y[3]);
             }
             __syncthreads();
-            if (tid < T && tj > K) {
+            if (tile && tj > K) {
                 real li[16], lj[16];
-                const real* pi = Lt + tri(ti, K) * 16;
-                const real* pj = Lt + tri(tj, K) * 16;
+                const real* pi = Lt + tri(ti, K) * TS;
+                const real* pj = Lt + tri(tj, K) * TS;
 #pragma unroll
                 for (int t = 0; t < 16; t += 2) { ld2(pi + t, li[t], li[t + 1]); ld2(pj + t, lj[t], lj[t + 1]); }
 #pragma unroll
@@ -131,74 +194,93 @@ struct DenseCtx {
                         for (int c = 0; c < 4; ++c) s = fma(-li[q * 4 + c], lj[r * 4 + c], s);
                         acc[q * 4 + r] = s;
                     }
+                if (ti == K + 1 && tj == K + 1) {
+                    Chol4<real> L;
+                    L.factor(acc);
+                    Inv4<real> Ni;
+                    Ni.from(L);
+                    Ni.store(Lt + tid * TS);
+                }
+            } else if (rhs && J > K) {
+                real lj[16], y[4];
+                const real* pj = Lt + tri(J, K) * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
+                ld2(rt + 4 * K, y[0], y[1]); ld2(rt + 4 * K + 2, y[2], y[3]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r4[q] -= (lj[q * 4] * y[0] + lj[q * 4 + 1] * y[1]) + (lj[q * 4 + 2] * y[2] + lj[q * 4 + 3] * y[3]);
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
-    // warp 0: dst = K^-1 rhs with the factor in Lt (rows lane, lane+32, lane+64 per lane)
-    __device__ __forceinline__ void solve(const real* rhs, real* dst)
+    // warp 0, lane I < N owns block row I: dst = K^-1 rhs with the factor in Lt; fwd_done: rhs already holds Lam^-1 rhs
+    __device__ __forceinline__ void solve(const real* rhs, real* dst, const bool fwd_done)
     {
-        real r[3];
+        real r4[4] = {0, 0, 0, 0};
+        const bool row = lane < N;
+        if (row) { ld2(rhs + 4 * lane, r4[0], r4[1]); ld2(rhs + 4 * lane + 2, r4[2], r4[3]); }
+        if (!fwd_done) {
+            for (int K = 0; K < N; ++K) {
+                real l[16];
+                if (row && lane > K) {
+                    const real* p = Lt + tri(lane, K) * TS;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) { const int e = lane + 32 * m; r[m] = e < E ? rhs[e] : real(0); }
-        for (int K = 0; K < N; ++K) {
-            const int m0 = K >> 3, l0 = (4 * K) & 31;
-            const real rs = m0 == 0 ? r[0] : (m0 == 1 ? r[1] : r[2]);
-            real rk[4], yk[4];
+                    for (int t = 0; t < 16; t += 2) ld2(p + t, l[t], l[t + 1]);
+                } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rk[q] = __shfl_sync(FULL, rs, l0 + q);
-            Chol4<real> L;
-            L.load(Lt + tri(K, K) * 16);
-            L.fsolve(rk, yk);
+                    for (int t = 0; t < 16; ++t) l[t] = 0;
+                }
+                Inv4<real> Ni;
+                Ni.load(Lt + tri(K, K) * TS);
+                real rk[4], y[4];
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const int e = lane + 32 * m, I = e >> 2;
-                if (e < E) {
-                    if (I == K) r[m] = sel4(yk, e & 3);
-                    else if (I > K) {
-                        const real* p = Lt + tri(I, K) * 16 + (e & 3) * 4;
-                        real l0_, l1_, l2_, l3_;
-                        ld2(p, l0_, l1_); ld2(p + 2, l2_, l3_);
-                        r[m] -= l0_ * yk[0] + l1_ * yk[1] + l2_ * yk[2] + l3_ * yk[3];
-                    }
+                for (int q = 0; q < 4; ++q) rk[q] = __shfl_sync(FULL, r4[q], K);
+                Ni.mul(rk, y);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const real upd = r4[q] - ((l[q * 4] * y[0] + l[q * 4 + 1] * y[1]) + (l[q * 4 + 2] * y[2] + l[q * 4 + 3] * y[3]));
+                    r4[q] = lane == K ? y[q] : upd;
                 }
             }
         }
         for (int K = N - 1; K >= 0; --K) {
-            const int m0 = K >> 3, l0 = (4 * K) & 31;
-            const real rs = m0 == 0 ? r[0] : (m0 == 1 ? r[1] : r[2]);
-            real rk[4], xk[4];
+            real l[16];
+            if (lane < K) {
+                const real* p = Lt + tri(K, lane) * TS;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rk[q] = -__shfl_sync(FULL, rs, l0 + q);
-            Chol4<real> L;
-            L.load(Lt + tri(K, K) * 16);
-            L.bsolve_neg(rk, xk);                  // Lam^T x = y
+                for (int t = 0; t < 16; t += 2) ld2(p + t, l[t], l[t + 1]);
+            } else {
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const int e = lane + 32 * m, I = e >> 2;
-                if (e < E) {
-                    if (I == K) r[m] = sel4(xk, e & 3);
-                    else if (I < K) {
-                        const real* p = Lt + tri(K, I) * 16 + (e & 3);
-                        r[m] -= p[0] * xk[0] + p[4] * xk[1] + p[8] * xk[2] + p[12] * xk[3];
-                    }
-                }
+                for (int t = 0; t < 16; ++t) l[t] = 0;
+            }
+            Inv4<real> Ni;
+            Ni.load(Lt + tri(K, K) * TS);
+            real rk[4], x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rk[q] = __shfl_sync(FULL, r4[q], K);
+            Ni.mulT(rk, x);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const real upd = r4[c] - ((l[c] * x[0] + l[4 + c] * x[1]) + (l[8 + c] * x[2] + l[12 + c] * x[3]));
+                r4[c] = lane == K ? x[c] : upd;
             }
         }
-#pragma unroll
-        for (int m = 0; m < 3; ++m) { const int e = lane + 32 * m; if (e < E) dst[e] = r[m]; }
+        if (row) { st2(dst + 4 * lane, r4[0], r4[1]); st2(dst + 4 * lane + 2, r4[2], r4[3]); }
         __syncwarp();
     }
 };
 
 #ifdef QMPC_DENSE_PROF
-#define DPROF_DECL long long pf_t0 = clock64(), pf_last = pf_t0, pf_acc[6] = {0, 0, 0, 0, 0, 0}; int pf_n[6] = {0, 0, 0, 0, 0, 0}
+#define DPROF_DECL long long pf_t0 = clock64(), pf_last = pf_t0, pf_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int pf_n[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define DPROF(slot) { const long long pf_now = clock64(); pf_acc[slot] += pf_now - pf_last; ++pf_n[slot]; pf_last = pf_now; }
 #else
 #define DPROF_DECL
 #define DPROF(slot)
 #endif
+
+// element loop of warp 0: e = lane, lane + 32, lane + 64 (E <= 96), unrolled so the three elements overlap
+#define DN_FOR_E(e) _Pragma("unroll") for (int e##_m = 0; e##_m < 3; ++e##_m) for (int e = lane + 32 * e##_m; e < E; e = E)
 
 template <typename real>
 __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<real> da)
@@ -213,13 +295,17 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
     DenseCtx<real> c{a};
     c.tid = tid; c.lane = lane; c.N = N; c.E = E; c.T = T; c.GS = GS;
     c.Ht = sm + lay.Ht; c.Lt = sm + lay.Lt; c.G = sm + lay.G; c.ev = sm + lay.ev;
-    real* small = sm + lay.sml;                 // wv(16) xp(16) + control words
-    int* ctl = reinterpret_cast<int*>(small + 32);
+    real* sq = sm + lay.sq;                     // sqrt of the stage / terminal state weights
+    real* small = sm + lay.sml;                 // wv(16) xp(16) red(16) control words
+    real* red = small + 32;
+    int* ctl = reinterpret_cast<int*>(small + 48);
+    real* tb = sm + lay.tb;                     // two staged stage tiles (condensing)
+    real* dxs = sm + lay.dxs;                   // state increments of the roll-out [(N+1)][13]
     real* v = sm + lay.vec;
     c.f = v; c.ubar = v + E; c.ucur = v + 2 * E; c.tl = v + 3 * E; c.tu = v + 4 * E; c.ll = v + 5 * E; c.lu = v + 6 * E;
     c.cl = v + 7 * E; c.cu = v + 8 * E; c.ua = v + 9 * E; c.usol = v + 10 * E; c.rt = v + 11 * E; c.dR = v + 12 * E;
-    c.tv = v + 13 * E;
-    c.fx = c.cl; c.fv = c.cu; c.grad = c.ua;
+    c.tv = v + 13 * E; c.itl = v + 14 * E; c.itu = v + 15 * E; c.ill = v + 16 * E; c.ilu = v + 17 * E;
+    c.fx = c.cl; c.fv = c.cu;
     {   // tile owned by this thread
         int i = 0;
         while ((i + 1) * (i + 2) / 2 <= tid) ++i;
@@ -228,11 +314,13 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
     const int ti = c.ti, tj = c.tj;
     const int count = da.hard_list ? *da.hard_count : a.B;
     const real lb = a.lb, ub = a.ub;
-    enum { T_FIXED, T_ADJ, T_PRED, T_CORR, T_GRAD, T_DONE };
+    if (tid < NX) { sq[tid] = sqrt(a.Qd[tid]); sq[16 + tid] = sqrt(a.QNd[tid]); }
+    enum { T_FIXED, T_ADJ, T_PRED, T_GRAD, T_DONE };
 
     for (int item = blockIdx.x; item < count; item += gridDim.x) {
         const int ocp = da.hard_list ? da.hard_list[item] : item;
         if (a.timeline && tid == 0) a.timeline[2 * ocp] = global_ns();
+        DPROF_DECL;
         const real* Wv = a.W + (size_t)ocp * N * WT;
         const double* x0 = a.x0 + (size_t)ocp * NX;
         const double* yref = a.yref + (size_t)ocp * N * NY;
@@ -241,11 +329,16 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
         double* uit = a.uit + (size_t)ocp * N * NU;
         unsigned char* actset = a.act + (size_t)ocp * E;
 
-        DPROF_DECL;
-        // ---- condensing
-        for (int idx = tid; idx < 13 * GS; idx += DN_THREADS) c.G[idx] = 0;
-        __syncthreads();
-        if (tid < NX) c.G[tid * GS + E] = real(x0[tid] - xit[tid]);
+        // ---- condensing: thread c < E carries impulse-response column c, thread E the free response; thread t < T
+        //      accumulates tile t of H = Rbar + sum_k G_k' Q_k G_k from the sqrt(Q)-scaled columns in shared memory
+        if (tid < WT) tb[tid] = __ldg(Wv + tid);
+        for (int idx = NX + tid; idx < (N + 1) * NX; idx += DN_THREADS) {     // iterate minus reference, stages 1..N
+            const int k = idx / NX, r = idx - k * NX;
+            dxs[idx] = real(xit[idx] - (k < N ? yref[(size_t)k * NY + r] : yref_e[r]));
+        }
+        real g[NX];
+#pragma unroll
+        for (int r = 0; r < NX; ++r) g[r] = tid == E ? real(x0[r] - xit[r]) : real(0);
         if (tid < E) {
             const real ub_ = real(uit[tid]);
             c.ubar[tid] = ub_;
@@ -257,57 +350,59 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
         real fc = 0;
         __syncthreads();
         for (int k = 0; k < N; ++k) {
-            const real* tile = Wv + (size_t)k * WT;
+            const real* tile = tb + (k & 1) * WT;
             const bool colact = (tid < E && (tid >> 2) <= k) || tid == E;
-            real gn[NX];
+            const real* sqk = sq + ((k + 1 < N) ? 0 : 16);
+            // next stage's tile is fetched while this stage computes
+            real wnext = 0;
+            if (k + 1 < N && tid < WT) wnext = __ldg(Wv + (size_t)(k + 1) * WT + tid);
             if (colact) {
                 if (tid < E && (tid >> 2) == k) {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) gn[r] = __ldg(tile + r * 16 + (tid & 3));
+                    for (int r = 0; r < NX; ++r) g[r] = tile[r * 16 + (tid & 3)];
                 } else {
-                    real g[NX];
-#pragma unroll
-                    for (int s = 0; s < NX; ++s) g[s] = c.G[s * GS + tid];
+                    real gn[NX];
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
                         real s0 = r < 3 ? g[r] : real(0), s1 = 0;
 #pragma unroll
                         for (int s = 0; s < 10; s += 2) {
                             real t0, t1;
-                            ldg2(tile + r * 16 + 4 + s, t0, t1);
-                            s0 += t0 * g[3 + s]; s1 += t1 * g[4 + s];
+                            ld2(tile + r * 16 + 4 + s, t0, t1);
+                            s0 = fma(t0, g[3 + s], s0); s1 = fma(t1, g[4 + s], s1);
                         }
                         gn[r] = s0 + s1;
                     }
                     if (tid == E) {
 #pragma unroll
-                        for (int r = 0; r < NX; ++r) gn[r] += __ldg(tile + r * 16 + 14);
+                        for (int r = 0; r < NX; ++r) gn[r] += tile[r * 16 + 14];
                     }
+#pragma unroll
+                    for (int r = 0; r < NX; ++r) g[r] = gn[r];
                 }
             }
-            __syncthreads();                    // every read of the previous G is done
+            DPROF(7);
+            __syncthreads();                    // the tile accumulation of the previous stage has read G
+            DPROF(8);
             if (colact) {
+                if (tid < E) {
 #pragma unroll
-                for (int r = 0; r < NX; ++r) c.G[r * GS + tid] = gn[r];
-                if (tid == E) {
+                    for (int r = 0; r < NX; ++r) c.G[r * GS + tid] = sqk[r] * g[r];
+                } else {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) {
-                        const real w = (k + 1 < N) ? a.Qd[r] : a.QNd[r];
-                        const double ref = (k + 1 < N) ? yref[(size_t)(k + 1) * NY + r] : yref_e[r];
-                        c.ev[r] = w * (gn[r] + real(xit[(size_t)(k + 1) * NX + r] - ref));
-                    }
+                    for (int r = 0; r < NX; ++r) c.ev[r] = sqk[r] * (g[r] + dxs[(k + 1) * NX + r]);
                 }
             }
+            if (k + 1 < N && tid < WT) tb[((k + 1) & 1) * WT + tid] = wnext;
+            DPROF(9);
             __syncthreads();
-            if (tid < T && ti <= k) {           // H tile += G_i' Q G_j
+            DPROF(10);
+            if (tid < T && ti <= k) {           // H tile += (sqrt(Q) G_i)' (sqrt(Q) G_j)
 #pragma unroll
                 for (int r = 0; r < NX; ++r) {
-                    const real w = (k + 1 < N) ? a.Qd[r] : a.QNd[r];
                     real gi[4], gj[4];
                     ld2(c.G + r * GS + 4 * ti, gi[0], gi[1]); ld2(c.G + r * GS + 4 * ti + 2, gi[2], gi[3]);
                     ld2(c.G + r * GS + 4 * tj, gj[0], gj[1]); ld2(c.G + r * GS + 4 * tj + 2, gj[2], gj[3]);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) gj[q] *= w;
 #pragma unroll
                     for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -316,58 +411,53 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
             }
             if (tid < E && (tid >> 2) <= k) {
 #pragma unroll
-                for (int r = 0; r < NX; ++r) fc = fma(gn[r], c.ev[r], fc);
+                for (int r = 0; r < NX; ++r) fc = fma(sqk[r] * g[r], c.ev[r], fc);
             }
+            DPROF(11);
         }
         if (tid < T) {
             if (ti == tj) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[q * 5] += a.Rd[q];
             }
-            real* o = c.Ht + tid * 16;
+            real* o = c.Ht + tid * TS;
 #pragma unroll
-            for (int t = 0; t < 16; ++t) o[t] = acc[t];
+            for (int t = 0; t < 16; t += 2) st2(o + t, acc[t], acc[t + 1]);
         }
-        if (tid < E) c.f[tid] += fc;
+        if (tid < E) {
+            c.f[tid] += fc;
+            c.usol[tid] = real(0.5) * (lb + ub) - c.ubar[tid];
+        }
         if (tid == 0) ctl[0] = T_GRAD;
         __syncthreads();
         DPROF(0);
 
         // ---- box-QP: warp 0 drives (element-wise work, triangular solves, decisions); the CTA factors and multiplies
         int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
-        bool exact = false, refine = a.max_refine > 0, ipm_started = false;
-        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, cpass = 0;
-        real target = refine ? a.mu_switch : a.mu_tol, mu = 0, sigma = 0, so = 1, resfac = 1;
+        bool exact = false, refine = a.max_refine > 0;
+        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0;
+        real target = refine ? a.mu_switch : a.mu_tol, mu = 0, resfac = 1;
         const real inv2E = real(1) / real(2 * E);
         int trip = T_GRAD;
-        if (warp == 0) {
-            for (int e = lane; e < E; e += 32) c.usol[e] = real(0.5) * (lb + ub) - c.ubar[e];
-        }
-        __syncthreads();
         while (true) {
             trip = ctl[0];
             if (trip == T_DONE) break;
             DPROF(5);
             // (1) products with H
             if (trip == T_GRAD || trip == T_ADJ) { c.matvec(c.usol); __syncthreads(); }
-            else if (trip == T_FIXED) {
-                if (warp == 0) {
-                    for (int e = lane; e < E; e += 32)
-                        c.fv[e] = c.fx[e] == real(1) ? lb - c.ubar[e] : (c.fx[e] == real(2) ? ub - c.ubar[e] : real(0));
-                }
-                __syncthreads();
-                c.matvec(c.fv);
-                __syncthreads();
-            }
+            else if (trip == T_FIXED) { c.matvec(c.fv); __syncthreads(); }
             DPROF(1);
             // (2) right-hand side, factorisation
             if (trip == T_FIXED || trip == T_PRED) {
                 if (warp == 0) {
                     if (trip == T_FIXED) {
-                        for (int e = lane; e < E; e += 32) c.rt[e] = c.fx[e] != real(0) ? c.fv[e] : -c.f[e] - c.tv[e];
+                        DN_FOR_E(e) c.rt[e] = c.fx[e] != real(0) ? c.fv[e] : -c.f[e] - c.tv[e];
                     } else {
-                        for (int e = lane; e < E; e += 32) {
-                            const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];
+                        DN_FOR_E(e) {
+                            const real itl = real(1) / c.tl[e], itu = real(1) / c.tu[e];
+                            const real ll = c.ll[e], lu = c.lu[e];
+                            c.itl[e] = itl; c.itu[e] = itu; c.ill[e] = real(1) / ll; c.ilu[e] = real(1) / lu;
+                            const real d = ll * itl + lu * itu;
                             c.dR[e] = d;
                             c.rt[e] = -c.f[e] + d * (c.ucur[e] - c.ubar[e]);
                         }
@@ -382,27 +472,29 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                 int next = T_DONE;
                 if (trip == T_GRAD) {
                     real gs = 0;
-                    for (int e = lane; e < E; e += 32) gs += fabs(c.tv[e] + c.f[e]);
+                    DN_FOR_E(e) gs += fabs(c.tv[e] + c.f[e]);
                     gs = warp_sum(gs) / real(E);
                     const real lam0 = rfinite(gs) ? fmin(fmax(a.lam0_scale * gs, a.lam0_min), a.lam0_max) : a.lam0_min;
-                    for (int e = lane; e < E; e += 32) {
+                    DN_FOR_E(e) {
                         const real u0 = real(0.5) * (lb + ub);
                         c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0; c.ll[e] = lam0; c.lu[e] = lam0;
                     }
-                    ipm_started = true;
                     next = T_PRED;
                 } else if (trip == T_FIXED) {
-                    c.solve(c.rt, c.usol);
+                    c.solve(c.rt, c.usol, true);
                     next = T_ADJ;
                 } else if (trip == T_ADJ) {
                     ++rounds;
                     int changed = 0;
-                    for (int e = lane; e < E; e += 32) {
+                    DN_FOR_E(e) {
                         const real fxe = c.fx[e], un = c.ubar[e] + c.usol[e], gr = c.tv[e] + c.f[e];
-                        if (fxe == real(1)) { if (gr < -a.refine_gtol) { c.fx[e] = 0; ++changed; } }
-                        else if (fxe == real(2)) { if (gr > a.refine_gtol) { c.fx[e] = 0; ++changed; } }
-                        else if (un < lb) { c.fx[e] = 1; ++changed; }
-                        else if (un > ub) { c.fx[e] = 2; ++changed; }
+                        real fn = fxe;
+                        if (fxe == real(1)) { if (gr < -a.refine_gtol) fn = 0; }
+                        else if (fxe == real(2)) { if (gr > a.refine_gtol) fn = 0; }
+                        else if (un < lb) fn = 1;
+                        else if (un > ub) fn = 2;
+                        if (fn != fxe) { ++changed; c.fx[e] = fn; }
+                        c.fv[e] = fn == real(1) ? lb - c.ubar[e] : (fn == real(2) ? ub - c.ubar[e] : real(0));
                     }
                     changed = warp_sum(changed);
                     ++round_no;
@@ -410,56 +502,54 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                     else if (--rounds_left > 0 && !(round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; next = T_FIXED; }
                     else { refine = false; target = a.mu_tol; next = T_PRED; }
                 } else if (trip == T_PRED) {
-                    c.solve(c.rt, c.usol);
-                    real apm = 1, adm = 1;
-                    for (int e = lane; e < E; e += 32) {
-                        const real tl = c.tl[e], tu = c.tu[e];
-                        const real du = c.ubar[e] + c.usol[e] - c.ucur[e];
-                        const real dl = -c.ll[e] - c.ll[e] / tl * du;
-                        const real dv = -c.lu[e] + c.lu[e] / tu * du;
-                        c.ua[e] = c.usol[e];
+                    DPROF(6);
+                    c.solve(c.rt, c.usol, true);
+                    DPROF(3);
+                    // predictor: step lengths (as reciprocals: alpha = 1 / max ratio), centring parameter
+                    real rpm = 1, rdm = 1;
+                    DN_FOR_E(e) {
+                        const real itl = c.itl[e], itu = c.itu[e], ll = c.ll[e], lu = c.lu[e];
+                        const real us = c.usol[e];
+                        const real du = c.ubar[e] + us - c.ucur[e];
+                        const real dl = -ll - ll * itl * du;
+                        const real dv = -lu + lu * itu * du;
+                        c.ua[e] = us;
                         c.cl[e] = du * dl; c.cu[e] = -du * dv;
                         c.rt[e] = dl; c.tv[e] = dv;
-                        if (du < 0) apm = fmin(apm, -tl / du);
-                        if (du > 0) apm = fmin(apm, tu / du);
-                        if (dl < 0) adm = fmin(adm, -c.ll[e] / dl);
-                        if (dv < 0) adm = fmin(adm, -c.lu[e] / dv);
+                        rpm = fmax(rpm, fmax(-du * itl, du * itu));
+                        rdm = fmax(rdm, fmax(-dl * c.ill[e], -dv * c.ilu[e]));
                     }
-                    const real apa = warp_min(apm), ada = warp_min(adm);
+                    const real apa = real(1) / warp_max(rpm), ada = real(1) / warp_max(rdm);
                     real s = 0;
-                    for (int e = lane; e < E; e += 32) {
+                    DN_FOR_E(e) {
                         const real du = c.ubar[e] + c.ua[e] - c.ucur[e];
                         s += (c.ll[e] + ada * c.rt[e]) * (c.tl[e] + apa * du) + (c.lu[e] + ada * c.tv[e]) * (c.tu[e] - apa * du);
                     }
                     const real muaff = warp_sum(s) * inv2E;
-                    sigma = muaff / mu; sigma = sigma * sigma * sigma;
-                    so = 1; cpass = 0;
-                    next = T_CORR;
-                }
-                if (trip == T_CORR || next == T_CORR) {
-                    // corrector (increment on the predictor); blocked Mehrotra step -> once more as a centring step
-                    while (true) {
+                    real sigma = muaff / mu; sigma = sigma * sigma * sigma;
+                    // corrector (increment on the predictor); a blocked Mehrotra step is redone once as a centring step
+                    real so = 1;
+                    for (int cpass = 0; cpass < 2; ++cpass) {
                         const real smu = sigma * mu;
-                        for (int e = lane; e < E; e += 32)
-                            c.rt[e] = (smu - so * c.cl[e]) / c.tl[e] - (smu - so * c.cu[e]) / c.tu[e];
+                        DN_FOR_E(e) c.rt[e] = (smu - so * c.cl[e]) * c.itl[e] - (smu - so * c.cu[e]) * c.itu[e];
                         __syncwarp();
-                        c.solve(c.rt, c.usol);
-                        real apx = real(1e30), adx = real(1e30);
-                        for (int e = lane; e < E; e += 32) {
-                            const real tl = c.tl[e], tu = c.tu[e];
+                        DPROF(6);
+                        c.solve(c.rt, c.usol, false);
+                        DPROF(3);
+                        real rpx = real(1e-30), rdx = real(1e-30);
+                        DN_FOR_E(e) {
+                            const real itl = c.itl[e], itu = c.itu[e], ll = c.ll[e], lu = c.lu[e];
                             const real du = c.ubar[e] + c.ua[e] + c.usol[e] - c.ucur[e];
-                            const real dl = (smu - so * c.cl[e]) / tl - c.ll[e] - c.ll[e] / tl * du;
-                            const real dv = (smu - so * c.cu[e]) / tu - c.lu[e] + c.lu[e] / tu * du;
+                            const real dl = (smu - so * c.cl[e]) * itl - ll - ll * itl * du;
+                            const real dv = (smu - so * c.cu[e]) * itu - lu + lu * itu * du;
                             c.usol[e] = du; c.rt[e] = dl; c.tv[e] = dv;
-                            if (du < 0) apx = fmin(apx, -tl / du);
-                            if (du > 0) apx = fmin(apx, tu / du);
-                            if (dl < 0) adx = fmin(adx, -c.ll[e] / dl);
-                            if (dv < 0) adx = fmin(adx, -c.lu[e] / dv);
+                            rpx = fmax(rpx, fmax(-du * itl, du * itu));
+                            rdx = fmax(rdx, fmax(-dl * c.ill[e], -dv * c.ilu[e]));
                         }
-                        real ap = warp_min(apx), ad = warp_min(adx);
-                        if (cpass == 0 && fmin(ap, ad) < real(0.5)) { so = 0; sigma = fmax(sigma, real(0.5)); cpass = 1; continue; }
+                        real ap = real(1) / warp_max(rpx), ad = real(1) / warp_max(rdx);
+                        if (cpass == 0 && fmin(ap, ad) < real(0.5)) { so = 0; sigma = fmax(sigma, real(0.5)); continue; }
                         ap = fmin(real(1), real(0.995) * ap); ad = fmin(real(1), real(0.995) * ad);
-                        for (int e = lane; e < E; e += 32) {
+                        DN_FOR_E(e) {
                             const real du = ap * c.usol[e];
                             c.ucur[e] += du; c.tl[e] += du; c.tu[e] -= du;
                             c.ll[e] += ad * c.rt[e];
@@ -474,36 +564,40 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                 if (next == T_PRED) {           // complementarity, convergence / hand-over test
                     __syncwarp();
                     real s = 0;
-                    for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
+                    DN_FOR_E(e) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
                     mu = warp_sum(s) * inv2E;
                     if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; next = T_DONE; }
                     else if (mu < target && resfac < real(1e-3)) {
                         if (refine) {
-                            for (int e = lane; e < E; e += 32)
-                                c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
+                            DN_FOR_E(e) {
+                                const real fn = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
+                                c.fx[e] = fn;
+                                c.fv[e] = fn == real(1) ? lb - c.ubar[e] : (fn == real(2) ? ub - c.ubar[e] : real(0));
+                            }
                             next = T_FIXED; rounds_left = a.max_refine; prev_changed = 1 << 30; round_no = 0;
                         } else { status = QMPC_STATUS_OK_; next = T_DONE; }
                     } else if (it >= a.max_iter) next = T_DONE;
                 }
                 __syncwarp();
                 if (lane == 0) ctl[0] = next;
+                DPROF(6);
             }
-            DPROF(3);
             __syncthreads();
         }
-        // ---- result: new iterate, roll-out through the linearised dynamics (warp 0, lanes 0..15 carry the states)
+        // ---- result: new iterate, states re-rolled through the linearised dynamics
         if (warp == 0) {
             real chk = 0;
-            for (int e = lane; e < E; e += 32) { const real un = exact ? c.usol[e] : c.ucur[e]; chk += un - un; }
+            DN_FOR_E(e) { const real un = exact ? c.usol[e] : c.ucur[e]; chk += un - un; }
             chk = warp_sum(chk);
             if (!(chk == real(0))) status = QMPC_STATUS_NAN_;
             const bool good = status != QMPC_STATUS_NAN_;
+            if (lane == 0) ctl[1] = good ? 1 : 0;
             if (!good) {
-                for (int e = lane; e < E; e += 32) actset[e] = 255;
+                DN_FOR_E(e) actset[e] = 255;
                 if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(fmin(fmax(c.ubar[lane], lb), ub));
                 if (lane == 0) { a.cost[ocp] = nan(""); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
             } else {
-                for (int e = lane; e < E; e += 32) {
+                DN_FOR_E(e) {
                     real un;
                     unsigned char fl;
                     if (exact) {
@@ -515,30 +609,83 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                     }
                     actset[e] = fl;
                     c.ucur[e] = un;
+                    c.usol[e] = un - c.ubar[e];
+                    uit[e] = double(un);
                 }
-                __syncwarp();
-                for (int e = lane; e < E; e += 32) c.usol[e] = c.ucur[e] - c.ubar[e];
-            }
-            __syncwarp();
-            HalfCtx<real> hc{a};
-            hc.j = lane & 15; hc.N = N; hc.E = E; hc.hmask = 0xffffu << (lane & 16); hc.valid = lane < 16;
-            hc.sidx = -1;
-            hc.wv = small; hc.xp = small + 16; hc.usol = c.usol; hc.ubar = c.ubar;
-            hc.Wv = Wv; hc.x0 = x0; hc.yref = yref; hc.yref_e = yref_e; hc.xit = xit; hc.uit = uit;
-            real cost = hc.template forward<true>(0, false, good && lane < 16);
-            cost = hc.hsum(cost);
-            if (good) {
-                for (int e = lane; e < E; e += 32) uit[e] = double(c.ucur[e]);
                 if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(c.ucur[lane]);
-                if (lane == 0) { a.cost[ocp] = double(cost); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
+                __syncwarp();
+                // dx_{k+1} = A dx_k + B du_k + b_k, lane j < 13 = row j of the stage tile
+                real* wv = small;
+                real* xp = small + 16;
+                const int j = lane < NX ? lane : NX - 1;
+                if (lane < NX) {
+                    const real d0 = real(x0[lane] - xit[lane]);
+                    if (lane < 3) xp[lane] = d0; else wv[lane + 1] = d0;
+                } else if (lane == 14) wv[14] = 1;
+                else if (lane == 15) wv[15] = 0;
+                __syncwarp();
+                real wn[16];
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) ldg2(Wv + j * 16 + q, wn[q], wn[q + 1]);
+                for (int k = 0; k < N; ++k) {
+                    real wr[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) wr[q] = wn[q];
+                    if (k + 1 < N) {
+                        const real* tr = Wv + (size_t)(k + 1) * WT + j * 16;
+#pragma unroll
+                        for (int q = 0; q < 16; q += 2) ldg2(tr + q, wn[q], wn[q + 1]);
+                    }
+                    if (lane < 4) wv[lane] = c.usol[k * 4 + lane];
+                    __syncwarp();
+                    real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                        real v0, v1, v2, v3;
+                        ld2(wv + q, v0, v1); ld2(wv + q + 2, v2, v3);
+                        s0 = fma(wr[q], v0, s0); s1 = fma(wr[q + 1], v1, s1); s2 = fma(wr[q + 2], v2, s2); s3 = fma(wr[q + 3], v3, s3);
+                    }
+                    real accx = (s0 + s1) + (s2 + s3);
+                    if (lane < 3) accx += xp[lane];
+                    __syncwarp();
+                    if (lane < NX) {
+                        if (lane < 3) xp[lane] = accx; else wv[lane + 1] = accx;
+                        dxs[(k + 1) * NX + lane] = accx;
+                    }
+                    __syncwarp();
+                }
             }
-            if (a.timeline && lane == 0) a.timeline[2 * ocp + 1] = global_ns();
         }
+        __syncthreads();
         DPROF(4);
+        if (ctl[1]) {       // new states and objective, all threads
+            real cs = 0;
+            for (int idx = tid; idx < (N + 1) * NX; idx += DN_THREADS) {
+                const int k = idx / NX, r = idx - k * NX;
+                const double xnew = k == 0 ? x0[r] : xit[idx] + double(dxs[idx]);
+                xit[idx] = xnew;
+                const real w = k < N ? a.Qd[r] : a.QNd[r];
+                const real e_ = real(xnew - (k < N ? yref[(size_t)k * NY + r] : yref_e[r]));
+                cs += real(0.5) * w * e_ * e_;
+            }
+            if (tid < E) {
+                const real e_ = real(double(c.ucur[tid]) - yref[(size_t)(tid >> 2) * NY + NX + (tid & 3)]);
+                cs += real(0.5) * a.Rd[tid & 3] * e_ * e_;
+            }
+            cs = warp_sum(cs);
+            if (lane == 0) red[warp] = cs;
+            __syncthreads();
+            if (tid == 0) {
+                real tot = 0;
+                for (int w = 0; w < DN_THREADS / 32; ++w) tot += red[w];
+                a.cost[ocp] = double(tot); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds;
+            }
+        }
+        if (a.timeline && tid == 0) a.timeline[2 * ocp + 1] = global_ns();
 #ifdef QMPC_DENSE_PROF
         if (tid == 0 && item < 3)
-            printf("dense ocp %d it %d rounds %d | cycles: condense %lld | matvec %lld (%d) | factor %lld (%d) | warp0 solve+logic %lld (%d) | rollout %lld | loop-top %lld | total %lld\n",
-                   ocp, it, rounds, pf_acc[0], pf_acc[1], pf_n[1], pf_acc[2], pf_n[2], pf_acc[3], pf_n[3], pf_acc[4], pf_acc[5], clock64() - pf_t0);
+            printf("dense ocp %d it %d rounds %d | cycles: condense %lld | matvec %lld (%d) | factor %lld (%d) | solves %lld (%d) | logic %lld | rollout %lld | loop-top %lld | total %lld || condense: col %lld sync1 %lld store %lld sync2 %lld tile %lld\n",
+                   ocp, it, rounds, pf_acc[0], pf_acc[1], pf_n[1], pf_acc[2], pf_n[2], pf_acc[3], pf_n[3], pf_acc[6], pf_acc[4], pf_acc[5], clock64() - pf_t0, pf_acc[7], pf_acc[8], pf_acc[9], pf_acc[10], pf_acc[11]);
 #endif
         __syncthreads();
     }

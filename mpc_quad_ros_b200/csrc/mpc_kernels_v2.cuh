@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
     // trips: see qmpc_ipm_kernel; G_FWD/G_ADJ = roll-out + adjoint at the box centre that scales the IPM's start
     enum { T_FIXED, T_ADJ, T_PRED, T_CORR, T_GFWD, T_GADJ, T_DONE };
     int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
-    bool exact = false, refine = a.max_refine > 0, ipm_started = false;
+    bool exact = false, refine = a.max_refine > 0, ipm_started = false, handed = false;
     int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, trip = T_GFWD, cpass = 0;
     real target = refine ? a.mu_switch : a.mu_tol, mu = 0, sigma = 0, so = 1, resfac = 1;
     const real inv2E = real(1) / real(2 * E);
@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
         known = c.hmin(real(known)) > real(0.5) ? 1 : 0;
         if (known) { trip = T_FIXED; rounds_left = a.warm_rounds; }
     }
-    if (!valid) trip = T_DONE;
+    if (a.hard_count && trip == T_GFWD) { handed = true; trip = T_DONE; }
+    if (!valid) { trip = T_DONE; handed = false; }
 
     while (warp_any(trip != T_DONE)) {
         // ---- prepare this half's trip
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
             else if (--rounds_left > 0 && !(round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; trip = T_FIXED; }
             else {                                   // not settling: (re)enter the IPM
                 if (ipm_started) { refine = false; target = a.mu_tol; trip = T_PRED; }
+                else if (a.hard_count) { handed = true; trip = T_DONE; }     // screening mode: the dense kernel takes it
                 else trip = T_GFWD;
             }
         } else if (kP) {
@@ -552,14 +554,17 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
         __syncwarp();
     }
     // ---- result
-    if (valid) {
+    if (handed) {
+        if (j == 0) a.hard_list[atomicAdd(a.hard_count, 1)] = ocp;
+    }
+    if (valid && !handed) {
         real chk = 0;
         for (int e = j; e < E; e += 16) { const real un = exact ? c.usol[e] : (ipm_started ? c.ucur[e] : real(0)); chk += un - un; }
         chk = c.hsum(chk);
         if (!(chk == real(0)) || (!exact && !ipm_started)) status = QMPC_STATUS_NAN_;
     }
-    const bool good = valid && status != QMPC_STATUS_NAN_;
-    if (valid && !good) {
+    const bool good = valid && !handed && status != QMPC_STATUS_NAN_;
+    if (valid && !handed && !good) {
         for (int e = j; e < E; e += 16) actset[e] = 255;
         if (j < 4) a.u0[(size_t)ocp * 4 + j] = double(fmin(fmax(c.ubar[j], lb), ub));
         if (j == 0) { a.cost[ocp] = nan(""); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
@@ -588,7 +593,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
         if (j < 4) a.u0[(size_t)ocp * 4 + j] = double(c.ucur[j]);
         if (j == 0) { a.cost[ocp] = double(cost); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
     }
-    if (a.timeline && valid && j == 0) a.timeline[2 * ocp + 1] = global_ns();
+    if (a.timeline && valid && !handed && j == 0) a.timeline[2 * ocp + 1] = global_ns();
 }
 
 }  // namespace qmpc

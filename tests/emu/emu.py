@@ -50,6 +50,6 @@ def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None, variant=0
     status, iters, rounds = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     act = np.full((B, 4 * N), 255, dtype=np.uint8) if act is None else act
     W = np.empty((B, N, 13, 16), dtype=np.float32 if f32 else np.float64)
-    fn = getattr(lib(), "emu_solve%s_%s" % (("", "2", "3")[variant], "f32" if f32 else "f64"))
+    fn = getattr(lib(), "emu_solve%s_%s" % (("", "2", "3", "4")[variant], "f32" if f32 else "f64"))
     fn(C.byref(cfg), p(x0), p(yref), p(yref_e), p(alpha), p(xit), p(uit), p(u0), p(cost), p(status), p(iters), p(rounds), p(act), p(W))
     return dict(u0=u0, cost=cost, status=status, iters=iters, rounds=rounds, act=act, W=W)

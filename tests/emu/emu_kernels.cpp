@@ -29,11 +29,20 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
     if (variant == 0) {
         emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
                     [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
-    } else if (variant == 2) {      // screening kernel (warm-started rounds) + dense kernel for the rest
+    } else if (variant == 2 || variant == 3) {      // screening kernel (warm-started rounds) + dense kernel for the rest
         std::vector<int> list(B), cnt(1, 0);
         ia.hard_list = list.data(); ia.hard_count = cnt.data();
-        emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
-                    [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
+        if (variant == 2) {
+            emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
+                        [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
+        } else {
+            constexpr int W2 = 2;
+            std::vector<real> xtr((size_t)B * (N + 1) * NX), ws((size_t)B * 5 * 4 * N);
+            Ipm2Args<real> i2;
+            i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N); i2.xtr = xtr.data(); i2.ws = ws.data();
+            emu::launch((B + 2 * W2 - 1) / (2 * W2), W2 * 32, (size_t)2 * W2 * i2.b.smem_per_warp * sizeof(real),
+                        [&]() { qmpc_ipm2_kernel<real, W2>(i2); });
+        }
         DenseArgs<real> dn;
         dn.b = ia; dn.hard_list = list.data(); dn.hard_count = cnt.data();
         emu::launch(2, DN_THREADS, (size_t)dense_layout(N).total * sizeof(real), [&]() { qmpc_dense_kernel<real>(dn); });
@@ -85,4 +94,17 @@ extern "C" int emu_solve2_f32(const HostOcp* o, const double* x0, const double* 
                               int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
 {
     return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 1);
+}
+
+extern "C" int emu_solve4_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
+                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
+                              int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
+{
+    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 3);
+}
+extern "C" int emu_solve4_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
+                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
+                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
+{
+    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 3);
 }

