@@ -270,6 +270,8 @@ def b200_arm(a):
     torch.cuda.synchronize()
     ms_lin, ms_ipm, cnt = C.c_double(), C.c_double(), C.c_int()
     _capi.check(lib.qmpc_timing_read(loop2.opt._h, C.byref(ms_lin), C.byref(ms_ipm), C.byref(cnt)))
+    ms_dense = C.c_double()
+    _capi.check(lib.qmpc_timing_read_dense(loop2.opt._h, C.byref(ms_dense)))
     _capi.check(lib.qmpc_timing_enable(loop2.opt._h, 0))
     lat = np.array([evs[s].elapsed_time(evs[s + 1]) for s in range(a.steps)])
     # mean IPM iterations over a few sampled steps of a third short pass (host reads are outside any timed region)
@@ -297,7 +299,8 @@ def b200_arm(a):
                 "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
                 "peak_source": "measured in this run by qmpc_fma_peak (register-resident FMA microbenchmark); "
                                "MEASURED_PEAKS.json has no FMA figure",
-                "ms_per_launch": ipm_ms, "ms_linearize_per_launch": ms_lin.value / max(cnt.value, 1),
+                "ms_per_launch": ipm_ms, "ms_dense_per_launch": ms_dense.value / max(cnt.value, 1),
+                "ms_linearize_per_launch": ms_lin.value / max(cnt.value, 1),
                 "share_of_step": ipm_ms / float(lat.mean()) if lat.mean() > 0 else None,   # within the single-stream timing leg
                 "n_ipm_mean": n_ipm_mean, "n_refine_rounds_mean": n_rounds_mean, "n_factorisations_mean": n_fact,
                 "warm_start_success_frac": float(np.mean(n_warm_ok)) if n_warm_ok else None,

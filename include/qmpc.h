@@ -175,6 +175,9 @@ const double *qmpc_residual_y_device(qmpc_handle_t h);
 /* cudaEvents around the two kernels of qmpc_solve: enable, run solves, read summed device times (synchronises). */
 int qmpc_timing_enable(qmpc_handle_t h, int on);
 int qmpc_timing_read(qmpc_handle_t h, double *ms_linearize, double *ms_ipm, int *count);
+/* part of ms_ipm spent in the dense kernel (the solver is a screening launch followed by a dense launch); call before
+ * qmpc_timing_enable(h, 0) */
+int qmpc_timing_read_dense(qmpc_handle_t h, double *ms_dense);
 /* per-vehicle timeline of the solver kernel: when enabled, every OCP records %globaltimer (ns) when its warp starts
  * and when it has written its result; read copies [batch][2] (start, end) of the LAST solve to the host (synchronises). */
 int qmpc_timeline_enable(qmpc_handle_t h, int on);

@@ -22,6 +22,29 @@ __global__ void set_reference_kernel(int B, int N, const double* __restrict__ x_
     }
 }
 
+// A solve that ended with status != 0 (iteration limit or numerical breakdown) leaves an iterate that the next
+// linearisation cannot use (the vehicle has usually departed from its reference).  Before the next solve the SQP
+// iterate of such a vehicle is re-initialised on the new reference (states = reference, inputs = reference inputs)
+// and its remembered active set is dropped.  The reference implementation ignores acados' status (quad_opt.py:333);
+// this only acts where its behaviour is undefined.
+__global__ void reset_failed_kernel(int B, int N, const int* __restrict__ status, const double* __restrict__ yref,
+                                    const double* __restrict__ yref_e, double* __restrict__ xit, double* __restrict__ uit,
+                                    unsigned char* __restrict__ act)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * (N + 1)) return;
+    const int b = t / (N + 1), k = t - b * (N + 1);
+    if (status[b] == 0) return;
+    double* x = xit + ((size_t)b * (N + 1) + k) * NX;
+    if (k < N) {
+        const double* y = yref + ((size_t)b * N + k) * NY;
+        for (int c = 0; c < NX; ++c) x[c] = y[c];
+        for (int c = 0; c < NU; ++c) { uit[((size_t)b * N + k) * NU + c] = y[NX + c]; act[((size_t)b * N + k) * NU + c] = 255; }
+    } else {
+        for (int c = 0; c < NX; ++c) x[c] = yref_e[(size_t)b * NX + c];
+    }
+}
+
 // nominal RK4 step of the OCP model without GP (quad_optimizer.discrete_dynamics, quad_opt.py:353-377)
 __device__ __forceinline__ void rk4_nominal(const ModelParams<double>& mp, const double* x, const double* u, double dt,
                                             double* xn)

@@ -81,6 +81,7 @@ struct qmpc_solver {
     ModelParams<double> mp64;
     bool timing = false;              // cudaEvents around the two solve kernels (bench roofline leg only)
     std::vector<cudaEvent_t> ev;      // triples: before linearize, before ipm, after ipm
+    std::vector<cudaEvent_t> ev_mid;  // between the screening and the dense kernel (one per timed solve)
 };
 
 struct qrgp_model {
@@ -135,7 +136,8 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-    h->variant = getenv("QMPC_IPM_VARIANT") ? atoi(getenv("QMPC_IPM_VARIANT")) : 2;
+    h->variant = getenv("QMPC_IPM_VARIANT") ? atoi(getenv("QMPC_IPM_VARIANT")) : (h->cfg.precision == 64 ? 2 : 0);
+    if (h->cfg.precision != 64 && h->variant >= 2) h->variant -= 2;     // the condensed formulation is fp64-only
     const size_t smem2 = (size_t)2 * IPM2_WARPS * ipm2_smem_reals((int)N) * 8;
     if ((h->variant == 1 || h->variant == 3) && smem2 > 220 * 1024) h->variant = 0;
     if (h->variant == 1 || h->variant == 3) {
@@ -230,6 +232,7 @@ int qmpc_set_iterate(qmpc_handle_t h, const double* x, const double* u, void* st
     const size_t B = h->cfg.batch, N = h->cfg.n_nodes;
     int rc = copy_dd(h->xit, x, B * (N + 1) * NX * 8, stream);
     if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(h->status, 0, B * sizeof(int), S(stream)));      // an explicit iterate is never re-initialised
     return copy_dd(h->uit, u, B * N * NU * 8, stream);
 }
 
@@ -257,6 +260,11 @@ static int solve_impl(qmpc_solver* h, void* stream)
         CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1)); CU_TRY(cudaEventCreate(&e2));
         h->ev.push_back(e0); h->ev.push_back(e1); h->ev.push_back(e2);
         CU_TRY(cudaEventRecord(e0, S(stream)));
+    }
+    static const bool reset_failed = !(getenv("QMPC_RESET_ON_FAIL") && atoi(getenv("QMPC_RESET_ON_FAIL")) == 0);
+    if (reset_failed) {
+        reset_failed_kernel<<<cdiv((long long)B * (N + 1), 256), 256, 0, S(stream)>>>(B, N, h->status, h->yref, h->yref_e, h->xit, h->uit, h->act);
+        LAUNCH_CHECK();
     }
     qmpc_linearize_kernel<real><<<cdiv((long long)B * N * 16, 128), 128, 0, S(stream)>>>(la);
     LAUNCH_CHECK();
@@ -291,6 +299,12 @@ static int solve_impl(qmpc_solver* h, void* stream)
         } else
             qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
         LAUNCH_CHECK();
+        if (e2) {
+            cudaEvent_t em = nullptr;
+            CU_TRY(cudaEventCreate(&em));
+            h->ev_mid.push_back(em);
+            CU_TRY(cudaEventRecord(em, S(stream)));
+        }
         DenseArgs<real> dn;
         dn.b = ia; dn.hard_list = h->hard; dn.hard_count = h->hard + B;
         qmpc_dense_kernel<real><<<h->dense_grid, DN_THREADS, dense_layout(N).total * sizeof(real), S(stream)>>>(dn);
@@ -623,7 +637,8 @@ int qmpc_timing_enable(qmpc_handle_t h, int on)
 {
     if (!h) return fail(QMPC_ERR_ARG, "null handle");
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-    h->ev.clear();
+    for (cudaEvent_t e : h->ev_mid) cudaEventDestroy(e);
+    h->ev.clear(); h->ev_mid.clear();
     h->timing = on != 0;
     return QMPC_OK;
 }
@@ -647,6 +662,19 @@ int qmpc_timeline_read(qmpc_handle_t h, long long* out)
     if (!h->timeline) return fail(QMPC_ERR_ARG, "timeline not enabled");
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(out, h->timeline, (size_t)h->cfg.batch * 16, cudaMemcpyDeviceToHost));
+    return QMPC_OK;
+}
+int qmpc_timing_read_dense(qmpc_handle_t h, double* ms_dense)
+{
+    if (!h || !ms_dense) return fail(QMPC_ERR_ARG, "null argument");
+    CU_TRY(cudaDeviceSynchronize());
+    double d = 0;
+    for (size_t i = 0; i < h->ev_mid.size() && 3 * i + 2 < h->ev.size(); ++i) {
+        float t = 0;
+        CU_TRY(cudaEventElapsedTime(&t, h->ev_mid[i], h->ev[3 * i + 2]));
+        d += t;
+    }
+    *ms_dense = d;
     return QMPC_OK;
 }
 int qmpc_timing_read(qmpc_handle_t h, double* ms_lin, double* ms_ipm, int* count)

@@ -786,6 +786,13 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
             }
             const double *yref_e = chunk + (N - 1) * NX;
             if (use_gp) for (int d = 0; d < 3; ++d) orc_rgp_alpha(M, Kx_inv + d * M * M, mub + d * M, alpha + d * M);
+            if (have_pred[b] == 2) {      /* previous solve failed: restart the SQP iterate on the new reference */
+                for (int k = 0; k < N; ++k) {
+                    memcpy(xi + k * NX, chunk + k * NX, sizeof(double) * NX);
+                    for (int a = 0; a < NU; ++a) ui[k * NU + a] = u_ref;
+                }
+                memcpy(xi + N * NX, yref_e, sizeof(double) * NX);
+            }
             double xnow[NX], cost, kkt; int iters;
             memcpy(xnow, xb, sizeof(xnow));
             int st = orc_rti_step(quad, dt, N, use_gp ? M : 0, gpX, gpth, use_gp ? alpha : NULL, Wd, Wed, 0.0, 1.0,
@@ -807,7 +814,7 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
                     orc_rgp_regress(M, gpX + d * M, gpth + 3 * d, Kx_inv + d * M * M, mub + d * M, Cb + d * M * M, vb[d], ad[d]);
             }
             memcpy(xpred_prev + (size_t)b * NX, xpred, sizeof(xpred));
-            have_pred[b] = 1;
+            have_pred[b] = st > 1 ? 2 : 1;
         }
         free(yref); free(chunk); free(alpha);
     }

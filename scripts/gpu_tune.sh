@@ -6,7 +6,7 @@ run() { echo "## $QMPC_LIB $*" >> gpurun_out/tune.log; "$@" 2>> gpurun_out/tune.
 import json,sys
 d=json.loads(sys.stdin.read())
 r=d['roofline']
-print(json.dumps({k:d[k] for k in ('value','ms_per_step')}|{k:r[k] for k in ('ms_per_launch','ms_linearize_per_launch','n_ipm_mean','n_refine_rounds_mean','warm_start_success_frac','frac')}|{'p99':d['latency_ms']['p99'],'bad':d['solver']['status_not_ok_last_step']}))
+print(json.dumps({k:d[k] for k in ('value','ms_per_step')}|{k:r[k] for k in ('ms_per_launch','ms_dense_per_launch','ms_linearize_per_launch','n_ipm_mean','n_refine_rounds_mean','warm_start_success_frac','frac')}|{'p99':d['latency_ms']['p99'],'bad':d['solver']['status_not_ok_last_step']}))
 " >> gpurun_out/tune.log; }
 B="python bench.py --steps ${STEPS:-40} --warmup ${WARMUP:-10} --no-cpu-baseline --no-e2e"
 if [ "${TUNE_BASE:-1}" = "1" ]; then run $B; fi

@@ -36,6 +36,8 @@ def test_emulated_solve_matches_oracle(N, use_gp, variant):
 
 @VARIANTS
 def test_emulated_solve_fp32_within_1e4(variant):
+    if variant >= 2:
+        pytest.skip("fp32 handles use the Riccati kernel alone: the condensed Hessian (cond ~1e7) is an fp64-only formulation")
     B, N = 2, 10
     dt = 1.0 / N
     quad = orc.quad_hummingbird()
