@@ -295,7 +295,9 @@ def b200_arm(a):
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this
     # exact shape (profiles/r01_ipm_summary.txt); other shapes were not captured
     traffic = 341.0e6 if (B, N, M, a.precision, a.workload, a.cold) == (4096, 20, 20, 64, "random_smooth", False) else None
-    roofline = {"kernel": "qmpc_ipm_kernel", "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
+    roofline = {"kernel": "qmpc_ipm_kernel (warm-started Riccati screening) + qmpc_dense_kernel (condensed IPM/active-set for the rest)"
+                          if a.precision == 64 and N <= 21 else "qmpc_ipm_kernel",
+                "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
                 "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
                 "peak_source": "measured in this run by qmpc_fma_peak (register-resident FMA microbenchmark); "
                                "MEASURED_PEAKS.json has no FMA figure",

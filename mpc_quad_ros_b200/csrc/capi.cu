@@ -296,8 +296,11 @@ static int solve_impl(qmpc_solver* h, void* stream)
             i2.xtr = static_cast<real*>(h->xtr); i2.ws = static_cast<real*>(h->ws);
             const size_t smem2 = (size_t)2 * IPM2_WARPS * i2.b.smem_per_warp * sizeof(real) + pad;
             qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
-        } else
-            qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
+        } else {
+            ia.smem_per_warp = ipm_smem_reals_screen(N);
+            const size_t smem_s = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real) + pad;
+            qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem_s, S(stream)>>>(ia);
+        }
         LAUNCH_CHECK();
         if (e2) {
             cudaEvent_t em = nullptr;

@@ -29,6 +29,7 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
 
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
 inline int ipm_smem_reals(int N) { return (SM_VEC + SM_NVEC * 4 * N + (N + 1) * 13 + 9) & ~1; }
+inline int ipm_smem_reals_screen(int N) { return (SM_VEC + 7 * 4 * N + (N + 1) * 13 + 9) & ~1; }   // screening mode layout
 // two-OCPs-per-warp kernel: per-OCP reals, = 8 mod 16 so that the two OCPs of a warp sit half a bank row apart
 inline int ipm2_smem_reals(int N) { int n = 360 + 8 * 4 * N; n += (24 - (n % 16)) % 16; return n; }
 

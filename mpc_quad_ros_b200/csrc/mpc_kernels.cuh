@@ -683,9 +683,17 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     c.P = sm + SM_P; c.pv = sm + SM_PV; c.wv = sm + SM_WV; c.xp = sm + SM_XP; c.hv = sm + SM_HV;
     c.Ls = sm + SM_LS; c.cs = sm + SM_CS;
     real* v = sm + SM_VEC;
-    c.rt = v; c.dR = v + E; c.usol = v + 2 * E; c.ua = v + 3 * E; c.ucur = v + 4 * E; c.ll = v + 5 * E;
-    c.lu = v + 6 * E; c.ubar = v + 7 * E; c.rdel = v + 8 * E; c.cl = v + 9 * E; c.cu = v + 10 * E;
-    c.tl = v + 11 * E; c.tu = v + 12 * E; c.xtr = v + 13 * E;
+    if (a.hard_count) {
+        // screening mode never enters the IPM: only the 7 vectors of the active-set rounds are laid out (9.5 KB per OCP
+        // instead of 13.5 KB leaves ~100 KB of the SM's L1 for the stage tiles)
+        c.usol = v; c.ua = v + E; c.ucur = v + 2 * E; c.ubar = v + 3 * E; c.rdel = v + 4 * E; c.cl = v + 5 * E; c.cu = v + 6 * E;
+        c.xtr = v + 7 * E;
+        c.rt = c.dR = c.ll = c.lu = c.tl = c.tu = v;
+    } else {
+        c.rt = v; c.dR = v + E; c.usol = v + 2 * E; c.ua = v + 3 * E; c.ucur = v + 4 * E; c.ll = v + 5 * E;
+        c.lu = v + 6 * E; c.ubar = v + 7 * E; c.rdel = v + 8 * E; c.cl = v + 9 * E; c.cu = v + 10 * E;
+        c.tl = v + 11 * E; c.tu = v + 12 * E; c.xtr = v + 13 * E;
+    }
     c.fx = c.cl; c.fv = c.cu; c.grad = c.ua;
     c.Wv = a.W + (size_t)ocp * N * WT;
     c.facv = a.fac + (size_t)ocp * N * FAC;

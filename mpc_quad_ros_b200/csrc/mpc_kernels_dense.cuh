@@ -332,6 +332,9 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
         // ---- condensing: thread c < E carries impulse-response column c, thread E the free response; thread t < T
         //      accumulates tile t of H = Rbar + sum_k G_k' Q_k G_k from the sqrt(Q)-scaled columns in shared memory
         if (tid < WT) tb[tid] = __ldg(Wv + tid);
+        real w1 = 0, w2 = 0;                    // stage tiles k+1 and k+2, two stages of latency cover
+        if (tid < WT && 1 < N) w1 = __ldg(Wv + (size_t)WT + tid);
+        if (tid < WT && 2 < N) w2 = __ldg(Wv + (size_t)2 * WT + tid);
         for (int idx = NX + tid; idx < (N + 1) * NX; idx += DN_THREADS) {     // iterate minus reference, stages 1..N
             const int k = idx / NX, r = idx - k * NX;
             dxs[idx] = real(xit[idx] - (k < N ? yref[(size_t)k * NY + r] : yref_e[r]));
@@ -353,9 +356,6 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
             const real* tile = tb + (k & 1) * WT;
             const bool colact = (tid < E && (tid >> 2) <= k) || tid == E;
             const real* sqk = sq + ((k + 1 < N) ? 0 : 16);
-            // next stage's tile is fetched while this stage computes
-            real wnext = 0;
-            if (k + 1 < N && tid < WT) wnext = __ldg(Wv + (size_t)(k + 1) * WT + tid);
             if (colact) {
                 if (tid < E && (tid >> 2) == k) {
 #pragma unroll
@@ -393,7 +393,11 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                     for (int r = 0; r < NX; ++r) c.ev[r] = sqk[r] * (g[r] + dxs[(k + 1) * NX + r]);
                 }
             }
-            if (k + 1 < N && tid < WT) tb[((k + 1) & 1) * WT + tid] = wnext;
+            if (tid < WT) {
+                if (k + 1 < N) tb[((k + 1) & 1) * WT + tid] = w1;
+                w1 = w2;
+                if (k + 3 < N) w2 = __ldg(Wv + (size_t)(k + 3) * WT + tid);
+            }
             DPROF(9);
             __syncthreads();
             DPROF(10);
@@ -585,6 +589,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
             __syncthreads();
         }
         // ---- result: new iterate, states re-rolled through the linearised dynamics
+        for (int idx = tid; idx < N * NX; idx += DN_THREADS) prefetch_l1(Wv + (size_t)idx * 16);
         if (warp == 0) {
             real chk = 0;
             DN_FOR_E(e) { const real un = exact ? c.usol[e] : c.ucur[e]; chk += un - un; }

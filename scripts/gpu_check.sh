@@ -15,7 +15,7 @@ timeout 900 python bench.py --steps ${STEPS:-50} --warmup ${WARMUP:-5} ${BENCH_A
 tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 fi
 if [ "${NCU:-0}" = "1" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 70 -c 70 --csv --log-file gpurun_out/launches.csv env STEPS=20 python scripts/profile_step.py > gpurun_out/ncu_launches.log 2>&1
-STEPS=14 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qmpc_ipm -s 12 -c 1 -f -o gpurun_out/prof_ipm python scripts/profile_step.py > gpurun_out/ncu_ipm.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 270 -c 90 --csv --log-file gpurun_out/launches.csv env STEPS=42 python scripts/profile_step.py > gpurun_out/ncu_launches.log 2>&1
+STEPS=42 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:qmpc_ipm|qmpc_dense" -s 80 -c 2 -f -o gpurun_out/prof_ipm python scripts/profile_step.py > gpurun_out/ncu_ipm.log 2>&1
 tail -3 gpurun_out/ncu_ipm.log
 fi

@@ -1,4 +1,5 @@
-"""Summarise an .ncu-rep (first kernel): key raw metrics, SASS opcode mix and stall reasons.  usage: ncu_summary.py rep"""
+"""Summarise one kernel of an .ncu-rep: key raw metrics, SASS opcode mix and stall reasons.
+usage: ncu_summary.py rep [kernel-name-regex]"""
 import collections
 import csv
 import io
@@ -6,7 +7,8 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["-k", "regex:" + sys.argv[2]] if len(sys.argv) > 2 else []
+raw = subprocess.run(["ncu", "-i", rep] + ksel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, unit, vals = rows[0], rows[1], rows[2]
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -24,7 +26,7 @@ for k in keys:
     if k in hdr:
         i = hdr.index(k)
         print(f"{k:70s} {vals[i]} {unit[i]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + ksel + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr, data = rows[1], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}

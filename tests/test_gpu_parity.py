@@ -391,3 +391,60 @@ def test_grouped_streams_equal_single_stream():
     xg = torch.cat([lp.x for lp in grouped.loops]); ug = torch.cat([lp.u0 for lp in grouped.loops])
     mug = torch.cat([lp.opt.gpe.mu_tensor() for lp in grouped.loops])
     assert torch.equal(xg, single.x) and torch.equal(ug, single.u0) and torch.equal(mug, single.opt.gpe.mu_tensor())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_solver_kernel_variants_agree_with_oracle(variant, monkeypatch):
+    """QMPC_IPM_VARIANT selects the kernel mapping behind qmpc_solve (0 Riccati kernel alone, 1 two OCPs per warp,
+    2 = default: Riccati screening + dense condensed kernel, 3 two-OCP screening + dense).  Cold solve, then a warm-started
+    second solve from the returned iterate/active set: every mapping lands on the oracle's minimiser."""
+    monkeypatch.setenv("QMPC_IPM_VARIANT", str(variant))
+    B, N, M = 67, 20, 20                      # odd batch: idle half-warp / partial CTA paths
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(M)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=7, amp_choices=(8.0, 2.0, 0.5))
+    x, u, cost, st, it = _solve_batch(sc, B, N, gp)
+    xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
+    assert (st == 0).all(), st
+    assert u_rel(u, uo) < TOL_U64 and x_rel(x, xo) < TOL_X64
+    assert np.abs(cost - co).max() < 1e-7 * max(1.0, np.abs(co).max())
+
+
+@pytest.mark.gpu
+def test_failed_solve_reinitialises_iterate_on_reference():
+    """A vehicle whose solve breaks down (here: a non-finite iterate) holds its previous control, and before the next solve
+    its SQP iterate is re-initialised on the reference (aux_kernels.cuh reset_failed_kernel): the next solve is healthy
+    again and equals a solve started from that reference iterate.  The other vehicles are untouched."""
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    import ctypes as C
+    from mpc_quad_ros_b200 import _capi
+    B, N = 8, 20
+    dt = 1.0 / N
+    quadp = orc.quad_hummingbird()
+    sc = random_ocp_batch(B, N, dt, quadp, None, seed=11, amp_choices=(1.0,))
+    quad = Quadrotor3D(drag=True, batch=B).set_hummingbird_params()
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=None)
+    dev = opt.device
+    xit, uit = sc["xit"].copy(), sc["uit"].copy()
+    xit[3, 5, 2] = np.nan
+    opt.set_iterate(torch.as_tensor(xit), torch.as_tensor(uit))
+    yref = torch.as_tensor(sc["yref"], device=dev).contiguous()
+    yref_e = torch.as_tensor(sc["yref_e"], device=dev).contiguous()
+    _capi.check(_capi.lib().qmpc_set_yref(opt._h, _capi.ptr(yref), _capi.ptr(yref_e), _capi.stream_ptr()))
+    x0 = torch.as_tensor(sc["x0"], device=dev)
+    opt.run_optimization(x0)
+    st, _ = opt.solver_status()
+    assert st.cpu().numpy().tolist() == [0, 0, 0, 2, 0, 0, 0, 0]
+    x1, u1 = (t.cpu().numpy() for t in opt.get_iterate())
+    # second solve: vehicle 3 restarts from (reference states, reference inputs)
+    opt.run_optimization(x0)
+    st2, _ = opt.solver_status()
+    assert (st2.cpu().numpy() == 0).all()
+    x2, u2 = (t.cpu().numpy() for t in opt.get_iterate())
+    xr, ur = x1.copy(), u1.copy()
+    xr[3, :N] = sc["yref"][3, :, :13]; xr[3, N] = sc["yref_e"][3]; ur[3] = sc["yref"][3, :, 13:]
+    sc2 = dict(sc); sc2["xit"], sc2["uit"] = xr, ur
+    xo, uo, _, _ = oracle_solve_batch(sc2, quadp, dt, N, None)
+    assert u_rel(u2, uo) < TOL_U64 and x_rel(x2, xo) < TOL_X64
