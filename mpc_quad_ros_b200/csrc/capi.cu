@@ -157,7 +157,10 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
         if (h->cfg.precision == 64) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<double>, DN_THREADS, smemd));
         else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<float>, DN_THREADS, smemd / 2));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        h->dense_grid = (int)std::min<size_t>(B, (size_t)std::max(1, per_sm) * sms);
+        // persistent CTAs looping over the hard list: about 5 % of the vehicles are on it in steady state, so a sixth of
+        // the batch (at most one resident wave) covers it without queueing empty CTAs behind other streams' kernels
+        const size_t want = getenv("QMPC_DENSE_GRID") ? (size_t)atol(getenv("QMPC_DENSE_GRID")) : std::max<size_t>(32, B / 6);
+        h->dense_grid = (int)std::min<size_t>(std::min<size_t>(B, want), (size_t)std::max(1, per_sm) * sms);
     }
     CU_TRY(cudaDeviceSynchronize());
     *out = h;
