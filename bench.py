@@ -310,6 +310,15 @@ def b200_arm(a):
                 "algorithmic_flops_per_vehicle_step": flops_per_step(N, M, n_fact),
                 "whole_step_tflops": value / world * flops_per_step(N, M, n_fact) / 1e12}
 
+    # ---------------- secondary roofline: the linearisation kernel (K1), the one FMA-throughput-bound kernel of the step
+    lin_ms = ms_lin.value / max(cnt.value, 1)
+    lin_flops = B * N * (22116 + 108 * M)
+    lin_ach = lin_flops / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
+    roofline_lin = {"kernel": "qmpc_linearize_kernel", "bound": "fp%d_fma" % a.precision, "achieved": lin_ach, "peak": peak.value,
+                    "unit": "TFLOP/s", "frac": lin_ach / peak.value if peak.value else None, "traffic": None,
+                    "ms_per_launch": lin_ms, "note": "algorithmic flops N*(22116+108M) per vehicle (SURVEY 8d); ncu: fp64 pipe 45 % busy "
+                                                      "(redundant primal evaluation per sensitivity column, double-precision exp of the RBF)"}
+
     # ---------------- secondary roofline: the HBM-bound RGP update (K3), timed alone with CUDA events
     roofline_rgp = None
     if M and not a.shared_rgp:
@@ -431,7 +440,7 @@ def b200_arm(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f%d" % a.precision, "data": "synthetic", "config": workload_config(a, world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_rgp": roofline_rgp, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_linearize": roofline_lin, "roofline_rgp": roofline_rgp, "cpu_baseline": cpu,
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
                 "solver": {"status_not_ok_last_step": bad, "ipm_iters_mean": n_ipm_mean, "refine_rounds_mean": n_rounds_mean,
                            "warm_start": (not a.cold)}}

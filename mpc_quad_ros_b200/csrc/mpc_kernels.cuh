@@ -870,7 +870,25 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     }
     for (int e = lane; e < E; e += 32) c.usol[e] = c.ucur[e] - c.ubar[e];
     __syncwarp();
-    real cost = c.template forward<2>();
+    real cost = 0;
+    if (exact) {
+        // the pinned forward sweep of the last active-set round already holds the state increments of this solution
+        // (xtr): add them and evaluate the objective element-wise instead of rolling the horizon out once more
+        for (int idx = lane; idx < (N + 1) * NX; idx += 32) {
+            const int k = idx / NX, r = idx - k * NX;
+            const double xnew = k == 0 ? c.x0[r] : c.xit[idx] + double(c.xtr[idx]);
+            c.xit[idx] = xnew;
+            const real w = k < N ? a.Qd[r] : a.QNd[r];
+            const real e_ = real(xnew - (k < N ? c.yref[(size_t)k * NY + r] : c.yref_e[r]));
+            cost += real(0.5) * w * e_ * e_;
+        }
+        for (int e = lane; e < E; e += 32) {
+            const real e_ = real(double(c.ucur[e]) - c.yref[(size_t)(e >> 2) * NY + NX + (e & 3)]);
+            cost += real(0.5) * a.Rd[e & 3] * e_ * e_;
+        }
+    } else {
+        cost = c.template forward<2>();
+    }
     cost = warp_sum(cost);
     for (int e = lane; e < E; e += 32) c.uit[e] = double(c.ucur[e]);
     if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(c.ucur[lane]);
