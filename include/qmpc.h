@@ -171,6 +171,22 @@ int qmpc_closed_loop_step(qmpc_handle_t h, qrgp_handle_t g, const double *traj, 
 const double *qmpc_residual_x_device(qmpc_handle_t h);
 const double *qmpc_residual_y_device(qmpc_handle_t h);
 
+/* ---- RGP* hyper-parameter learning: RGP.learn (src/gp/RGP.py:332-482, sigma points :485-505) for n_models independent
+ * 1-D models on one basis grid X[n_basis] (host) with initial hyper-parameters theta[3] = (L, sigma_f, sigma_n) (host).
+ * State per model as RGP.__init__ leaves it (:141-157): mu_g = 0, C_g = K_x, mu_eta = theta, C_eta = I, C_g_eta = 0,
+ * K_x_inv = inv(K(X,X) + sigma_n^2 I).  The reference never calls learn from its control loop; neither does qmpc_step. */
+typedef struct qrgpl_model *qrgpl_handle_t;
+int qrgpl_create(int n_models, int n_basis, const double *X, const double *theta, int device, qrgpl_handle_t *out);
+int qrgpl_destroy(qrgpl_handle_t g);
+/* one learn() call per model: xt, yt device [n_models]; optional outputs mu_z [n][M+3], C_z [n][M+3][M+3] (device, may be NULL) */
+int qrgpl_learn(qrgpl_handle_t g, const double *xt, const double *yt, double *mu_z, double *C_z, void *stream);
+/* device copies of the state; any pointer may be NULL: mu_g [n][M], C_g [n][M][M], mu_eta [n][3], C_eta [n][3][3], Kx_inv [n][M][M] */
+int qrgpl_get_state(qrgpl_handle_t g, double *mu_g, double *C_g, double *mu_eta, double *C_eta, double *Kx_inv, void *stream);
+int qrgpl_set_state(qrgpl_handle_t g, const double *mu_g, const double *C_g, const double *mu_eta, const double *C_eta,
+                    const double *C_g_eta /*[n][M][3]*/, const double *Kx_inv, void *stream);
+/* per-model status of the last learn (device int [n]): 0 ok, 1 singular K_x */
+int qrgpl_get_status(qrgpl_handle_t g, int *status, void *stream);
+
 /* ---- measurement hooks (bench.py roofline leg; not part of the control path) */
 /* cudaEvents around the two kernels of qmpc_solve: enable, run solves, read summed device times (synchronises). */
 int qmpc_timing_enable(qmpc_handle_t h, int on);

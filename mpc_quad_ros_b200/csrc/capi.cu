@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC capi.cu -o libqmpc.so
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -88,6 +89,12 @@ struct qrgp_model {
     int B, M, device;
     double *X = nullptr, *theta = nullptr, *Kx = nullptr, *Kx_inv = nullptr;
     double *mu = nullptr, *C = nullptr, *alpha = nullptr, *xt = nullptr, *yt = nullptr;
+};
+
+struct qrgpl_model {
+    int n, M, device;
+    double *X = nullptr, *mu_g = nullptr, *C_g = nullptr, *mu_eta = nullptr, *C_eta = nullptr, *C_g_eta = nullptr, *Kx_inv = nullptr;
+    int* status = nullptr;
 };
 
 extern "C" {
@@ -293,6 +300,9 @@ static int solve_impl(qmpc_solver* h, void* stream)
         CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
         ia.hard_list = h->hard; ia.hard_count = h->hard + B;
         if (ia.warm_rounds > screen_rounds) ia.warm_rounds = screen_rounds;
+        static const int bail_round = getenv("QMPC_BAIL_ROUND") ? atoi(getenv("QMPC_BAIL_ROUND")) : 2;
+        static const int bail_changed = getenv("QMPC_BAIL_CHANGED") ? atoi(getenv("QMPC_BAIL_CHANGED")) : (1 << 20);
+        ia.bail_round = bail_round; ia.bail_changed = bail_changed;
         if (h->variant == 3) {
             Ipm2Args<real> i2;
             i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N);
@@ -635,6 +645,117 @@ int qmpc_closed_loop_step(qmpc_handle_t h, qrgp_handle_t g, const double* traj, 
     rc = qmpc_step(h, g, x, chunk, x_pred_prev, idx == 0, u0, stream);
     if (rc) return rc;
     return qmpc_plant_period(h->cfg.quad, plant, B, x, u0, sim_dt, n_sub, stream);
+}
+
+// ------------------------------------------------------------------------------------------- RGP* learning
+
+int qrgpl_create(int n_models, int n_basis, const double* X, const double* theta, int device, qrgpl_handle_t* out)
+{
+    if (!X || !theta || !out) return fail(QMPC_ERR_ARG, "null argument");
+    if (n_models < 1 || n_basis < 1 || n_basis > 64) return fail(QMPC_ERR_ARG, "n_models / n_basis out of range (n_basis <= 64)");
+    CU_TRY(cudaSetDevice(device));
+    const size_t n = n_models, M = n_basis;
+    // prior exactly as RGP.__init__: K_x = K(X,X) + sn^2 I, inverse by Gauss-Jordan with partial pivoting (host, once)
+    std::vector<double> Kx(M * M), W(M * 2 * M);
+    const double L = theta[0], sf = theta[1], sn = theta[2];
+    for (size_t i = 0; i < M; ++i)
+        for (size_t j = 0; j < M; ++j) {
+            const double e = X[i] - X[j];
+            const double k = sf * sf * std::exp(-0.5 * e * (1.0 / (L * L)) * e) + (i == j ? sn * sn : 0.0);
+            Kx[i * M + j] = k; W[i * 2 * M + j] = k; W[i * 2 * M + M + j] = (i == j);
+        }
+    for (size_t c = 0; c < M; ++c) {
+        size_t piv = c;
+        for (size_t i = c + 1; i < M; ++i) if (std::fabs(W[i * 2 * M + c]) > std::fabs(W[piv * 2 * M + c])) piv = i;
+        if (W[piv * 2 * M + c] == 0) return fail(QMPC_ERR_ARG, "K_x is singular");
+        if (piv != c) for (size_t j = 0; j < 2 * M; ++j) std::swap(W[c * 2 * M + j], W[piv * 2 * M + j]);
+        const double d = 1.0 / W[c * 2 * M + c];
+        for (size_t j = 0; j < 2 * M; ++j) W[c * 2 * M + j] *= d;
+        for (size_t i = 0; i < M; ++i) if (i != c) {
+            const double f = W[i * 2 * M + c];
+            if (f != 0) for (size_t j = 0; j < 2 * M; ++j) W[i * 2 * M + j] -= f * W[c * 2 * M + j];
+        }
+    }
+    std::vector<double> Kxi(M * M);
+    for (size_t i = 0; i < M; ++i) for (size_t j = 0; j < M; ++j) Kxi[i * M + j] = W[i * 2 * M + M + j];
+    qrgpl_model* g = new qrgpl_model();
+    g->n = n_models; g->M = n_basis; g->device = device;
+#define ALLOC(p, nb) CU_TRY(cudaMalloc(reinterpret_cast<void**>(&(p)), (nb)))
+    ALLOC(g->X, M * 8); ALLOC(g->mu_g, n * M * 8); ALLOC(g->C_g, n * M * M * 8); ALLOC(g->mu_eta, n * 3 * 8);
+    ALLOC(g->C_eta, n * 9 * 8); ALLOC(g->C_g_eta, n * M * 3 * 8); ALLOC(g->Kx_inv, n * M * M * 8); ALLOC(g->status, n * 4);
+#undef ALLOC
+    CU_TRY(cudaMemcpy(g->X, X, M * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemset(g->mu_g, 0, n * M * 8)); CU_TRY(cudaMemset(g->C_g_eta, 0, n * M * 3 * 8)); CU_TRY(cudaMemset(g->status, 0, n * 4));
+    std::vector<double> eta(n * 3), Ce(n * 9, 0.0);
+    for (size_t m = 0; m < n; ++m) { for (int k = 0; k < 3; ++k) { eta[m * 3 + k] = theta[k]; Ce[m * 9 + k * 4] = 1.0; } }
+    CU_TRY(cudaMemcpy(g->mu_eta, eta.data(), n * 3 * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g->C_eta, Ce.data(), n * 9 * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g->C_g, Kx.data(), M * M * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(g->Kx_inv, Kxi.data(), M * M * 8, cudaMemcpyHostToDevice));
+    for (size_t m = 1; m < n; ++m) {
+        CU_TRY(cudaMemcpyAsync(g->C_g + m * M * M, g->C_g, M * M * 8, cudaMemcpyDeviceToDevice, 0));
+        CU_TRY(cudaMemcpyAsync(g->Kx_inv + m * M * M, g->Kx_inv, M * M * 8, cudaMemcpyDeviceToDevice, 0));
+    }
+    const int smem = rgp_learn_smem_doubles(n_basis) * 8;
+    CU_TRY(cudaFuncSetAttribute(qrgp_learn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU_TRY(cudaDeviceSynchronize());
+    *out = g;
+    return QMPC_OK;
+}
+
+int qrgpl_destroy(qrgpl_handle_t g)
+{
+    if (!g) return QMPC_OK;
+    cudaSetDevice(g->device);
+    void* ps[] = {g->X, g->mu_g, g->C_g, g->mu_eta, g->C_eta, g->C_g_eta, g->Kx_inv, g->status};
+    for (void* p : ps) if (p) cudaFree(p);
+    delete g;
+    return QMPC_OK;
+}
+
+int qrgpl_learn(qrgpl_handle_t g, const double* xt, const double* yt, double* mu_z, double* C_z, void* stream)
+{
+    if (!g || !xt || !yt) return fail(QMPC_ERR_ARG, "null argument");
+    RgpLearnArgs a;
+    a.n_models = g->n; a.M = g->M; a.X = g->X; a.mu_g = g->mu_g; a.C_g = g->C_g; a.mu_eta = g->mu_eta; a.C_eta = g->C_eta;
+    a.C_g_eta = g->C_g_eta; a.Kx_inv = g->Kx_inv; a.mu_z = mu_z; a.C_z = C_z; a.xt = xt; a.yt = yt; a.status = g->status;
+    qrgp_learn_kernel<<<g->n, 128, rgp_learn_smem_doubles(g->M) * 8, S(stream)>>>(a);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qrgpl_get_state(qrgpl_handle_t g, double* mu_g, double* C_g, double* mu_eta, double* C_eta, double* Kx_inv, void* stream)
+{
+    if (!g) return fail(QMPC_ERR_ARG, "null handle");
+    const size_t n = g->n, M = g->M;
+    int rc = 0;
+    if (mu_g && !rc) rc = copy_dd(mu_g, g->mu_g, n * M * 8, stream);
+    if (C_g && !rc) rc = copy_dd(C_g, g->C_g, n * M * M * 8, stream);
+    if (mu_eta && !rc) rc = copy_dd(mu_eta, g->mu_eta, n * 3 * 8, stream);
+    if (C_eta && !rc) rc = copy_dd(C_eta, g->C_eta, n * 9 * 8, stream);
+    if (Kx_inv && !rc) rc = copy_dd(Kx_inv, g->Kx_inv, n * M * M * 8, stream);
+    return rc;
+}
+
+int qrgpl_set_state(qrgpl_handle_t g, const double* mu_g, const double* C_g, const double* mu_eta, const double* C_eta,
+                    const double* C_g_eta, const double* Kx_inv, void* stream)
+{
+    if (!g) return fail(QMPC_ERR_ARG, "null handle");
+    const size_t n = g->n, M = g->M;
+    int rc = 0;
+    if (mu_g && !rc) rc = copy_dd(g->mu_g, mu_g, n * M * 8, stream);
+    if (C_g && !rc) rc = copy_dd(g->C_g, C_g, n * M * M * 8, stream);
+    if (mu_eta && !rc) rc = copy_dd(g->mu_eta, mu_eta, n * 3 * 8, stream);
+    if (C_eta && !rc) rc = copy_dd(g->C_eta, C_eta, n * 9 * 8, stream);
+    if (C_g_eta && !rc) rc = copy_dd(g->C_g_eta, C_g_eta, n * M * 3 * 8, stream);
+    if (Kx_inv && !rc) rc = copy_dd(g->Kx_inv, Kx_inv, n * M * M * 8, stream);
+    return rc;
+}
+
+int qrgpl_get_status(qrgpl_handle_t g, int* status, void* stream)
+{
+    if (!g || !status) return fail(QMPC_ERR_ARG, "null argument");
+    return copy_dd(status, g->status, (size_t)g->n * 4, stream);
 }
 
 /* kernel timing for the roofline leg of bench.py: enable, run solves, then read (synchronises the device).

@@ -59,6 +59,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? 10 : c.refine_max_rounds);
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
+    a.bail_round = 2; a.bail_changed = 1 << 20;
     a.timeline = nullptr; a.hard_list = nullptr; a.hard_count = nullptr;
 }
 

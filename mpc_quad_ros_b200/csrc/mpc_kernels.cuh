@@ -128,6 +128,8 @@ struct IpmArgs {
     int max_iter;
     int max_refine;                // refinement rounds after the IPM; 0 = pure IPM down to mu_tol
     int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
+    int bail_round;                // rounds (0-based) from which a non-contracting change count ends the attempt (default 2)
+    int bail_changed;              // a round that still moves more inputs than this ends the attempt at once (default: never)
     int smem_per_warp;             // reals
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
@@ -569,7 +571,8 @@ struct WarpCtx {
             }
             changed = warp_sum(changed);
             if (!changed) return true;
-            if (round >= 2 && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
+            if (round >= a.bail_round && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
+            if (round >= 1 && changed > a.bail_changed) return false;
             prev_changed = changed;
         }
         return false;

@@ -291,4 +291,251 @@ __global__ void __launch_bounds__(256) qrgp_shared_apply_kernel(int M, const dou
     }
 }
 
+// ------------------------------------------------------------------------------------------ RGP* learning
+// RGP.learn (reference src/gp/RGP.py:332-482) with its sigma points (__draw_sigma_points :485-505): joint recursive
+// update of the basis-point estimate g and the hyper-parameters eta = (L, sigma_f, sigma_n) from one sample, restated
+// as the reference computes it, peculiarities included: At (hence Jt) is built once at the current hyper-parameters
+// and reused for every sigma point (:357-366, :392); the running mean of the cumulative sum is used inside the outer
+// product of the same iteration (:403-404); C_g_eta_t is never assigned by learn (:153); the exp() transform of eta
+// (:468-470) is overwritten by the plain assignment (:472-474).
+// One CTA per 1-D model; the (M+4)^2 joint covariance, the M x 2M Gauss-Jordan tableau of the new K_x and the vectors
+// live in shared memory, so M <= 64.
+struct RgpLearnArgs {
+    int n_models, M;
+    const double* X;        // [M] basis points (shared grid)
+    double* mu_g;           // [n][M]
+    double* C_g;            // [n][M][M]
+    double* mu_eta;         // [n][3]
+    double* C_eta;          // [n][3][3]
+    const double* C_g_eta;  // [n][M][3]   (never written by learn, like the reference)
+    double* Kx_inv;         // [n][M][M]
+    double* mu_z;           // [n][M+3]        return value of learn (may be null)
+    double* C_z;            // [n][M+3][M+3]   (may be null)
+    const double* xt;       // [n]
+    const double* yt;       // [n]
+    int* status;            // [n] 0 ok, 1 singular K_x
+};
+
+__host__ __device__ inline int rgp_learn_smem_doubles(int M) { return (M + 4) * (M + 4) + 3 * M * M + 14 * M + 64; }
+
+__device__ inline void sym3_sqrt_dev(const double* A, double* S)     // principal square root, cyclic Jacobi (thread 0)
+{
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = 0.5 * (A[i * 3 + j] + A[j * 3 + i]);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double th = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { const double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += v[i][k] * sqrt(a[k][k]) * v[j][k];
+            S[i * 3 + j] = acc;
+        }
+}
+
+// in-place Gauss-Jordan with partial pivoting on the n x 2n tableau W = [A | I] in shared memory (whole CTA)
+__device__ inline int gj_inverse_cta(int n, double* W, int* piv_sh)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, w2 = 2 * n;
+    for (int c = 0; c < n; ++c) {
+        if (tid == 0) {
+            int piv = c;
+            for (int i = c + 1; i < n; ++i) if (fabs(W[i * w2 + c]) > fabs(W[piv * w2 + c])) piv = i;
+            piv_sh[0] = W[piv * w2 + c] == 0.0 ? -1 : piv;
+        }
+        __syncthreads();
+        const int piv = piv_sh[0];
+        if (piv < 0) return 1;
+        if (piv != c) for (int j = tid; j < w2; j += nt) { const double t = W[c * w2 + j]; W[c * w2 + j] = W[piv * w2 + j]; W[piv * w2 + j] = t; }
+        __syncthreads();
+        const double d = 1.0 / W[c * w2 + c];
+        __syncthreads();
+        for (int j = tid; j < w2; j += nt) W[c * w2 + j] *= d;
+        __syncthreads();
+        // eliminate column c from the other rows; the multipliers are read before anybody overwrites column c
+        double* fcol = W + n * w2;              // n spare doubles behind the tableau
+        for (int i = tid; i < n; i += nt) fcol[i] = i == c ? 0.0 : W[i * w2 + c];
+        __syncthreads();
+        for (int e = tid; e < n * w2; e += nt) {
+            const int i = e / w2, j = e - i * w2;
+            const double f = fcol[i];
+            if (f != 0.0) W[e] -= f * W[c * w2 + j];
+        }
+        __syncthreads();
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) qrgp_learn_kernel(RgpLearnArgs a)
+{
+    extern __shared__ __align__(16) double lsm[];
+    const int model = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, M = a.M;
+    if (model >= a.n_models) return;
+    const int np_ = M + 4, nu_ = M + 2, nz = M + 3;
+    double* C_p = lsm;                         // (M+4)^2
+    double* Cgp = C_p + np_ * np_;             // M^2
+    double* W = Cgp + M * M;                   // M x 2M tableau (+ M spare)
+    double* kv = W + 2 * M * M + M;
+    double* Jt = kv + M; double* JC = Jt + M; double* cj = JC + M; double* vg = cj + M;
+    double* mu_p = vg + M; double* mu_pi = mu_p + np_; double* Lt = mu_pi + np_;       // Lt: 2(M+2)
+    double* St = Lt + 2 * nu_;                 // M x 3
+    double* sc = St + 3 * M;                   // scalars: [0..8] Ssq, [9..17] Cei, 18 Bv, 19 jcj, 20 jg
+    __shared__ int piv_sh[1];
+    const double* X = a.X;
+    double* mu_g = a.mu_g + (size_t)model * M;
+    double* C_g = a.C_g + (size_t)model * M * M;
+    double* mu_eta = a.mu_eta + (size_t)model * 3;
+    double* C_eta = a.C_eta + (size_t)model * 9;
+    const double* C_g_eta = a.C_g_eta + (size_t)model * M * 3;
+    double* Kxi = a.Kx_inv + (size_t)model * M * M;
+    const double xt = a.xt[model], yt = a.yt[model];
+    const double L = mu_eta[0], sf = mu_eta[1];
+    const double iL2 = 1.0 / (L * L), sf2 = sf * sf;
+    // ---- inference step
+    for (int i = tid; i < M; i += nt) kv[i] = rbf_k(xt, X[i], iL2, sf2);
+    for (int e = tid; e < np_ * np_; e += nt) C_p[e] = 0.0;
+    for (int i = tid; i < np_; i += nt) mu_p[i] = 0.0;
+    __syncthreads();
+    for (int j = tid; j < M; j += nt) { double s = 0; for (int i = 0; i < M; ++i) s += kv[i] * Kxi[i * M + j]; Jt[j] = s; }
+    if (tid == 0) {
+        double Ce[9], Wk[18];
+        for (int i = 0; i < 9; ++i) Ce[i] = C_eta[i];
+        // 3x3 inverse, Gauss-Jordan with partial pivoting
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Wk[i * 6 + j] = Ce[i * 3 + j]; Wk[i * 6 + 3 + j] = (i == j); }
+        for (int c = 0; c < 3; ++c) {
+            int piv = c;
+            for (int i = c + 1; i < 3; ++i) if (fabs(Wk[i * 6 + c]) > fabs(Wk[piv * 6 + c])) piv = i;
+            if (piv != c) for (int j = 0; j < 6; ++j) { const double t = Wk[c * 6 + j]; Wk[c * 6 + j] = Wk[piv * 6 + j]; Wk[piv * 6 + j] = t; }
+            const double d = 1.0 / Wk[c * 6 + c];
+            for (int j = 0; j < 6; ++j) Wk[c * 6 + j] *= d;
+            for (int i = 0; i < 3; ++i) if (i != c) { const double f = Wk[i * 6 + c]; if (f != 0) for (int j = 0; j < 6; ++j) Wk[i * 6 + j] -= f * Wk[c * 6 + j]; }
+        }
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sc[9 + i * 3 + j] = Wk[i * 6 + 3 + j];
+        double S6[9];
+        for (int i = 0; i < 9; ++i) S6[i] = (3.0 / (1.0 - 0.5)) * Ce[i];
+        sym3_sqrt_dev(S6, sc);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double jk = 0;
+        for (int j = 0; j < M; ++j) jk += Jt[j] * rbf_k(X[j], xt, iL2, sf2);
+        sc[18] = rbf_k(xt, xt, iL2, sf2) - jk;
+    }
+    for (int e = tid; e < M * 3; e += nt) {
+        const int i = e / 3, j = e - i * 3;
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += C_g_eta[i * 3 + k] * sc[9 + k * 3 + j];
+        St[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < M * M; e += nt) {
+        const int i = e / M, j = e - i * M;
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += St[i * 3 + k] * C_g_eta[j * 3 + k];
+        Cgp[e] = C_g[e] - s;
+    }
+    __syncthreads();
+    for (int j = tid; j < M; j += nt) {
+        double s = 0, t = 0;
+        for (int i = 0; i < M; ++i) { s += Jt[i] * Cgp[i * M + j]; t += Cgp[j * M + i] * Jt[i]; }
+        JC[j] = s; cj[j] = t;
+    }
+    __syncthreads();
+    if (tid == 0) { double s = 0; for (int j = 0; j < M; ++j) s += JC[j] * Jt[j]; sc[19] = s; }
+    __syncthreads();
+    // ---- unscented transform: 7 sigma points of eta, cumulative mean / covariance exactly in the reference's order
+    for (int sp = 0; sp < 7; ++sp) {
+        const double w = sp == 0 ? 0.5 : (1.0 - 0.5) / 6.0;
+        double eta[3];
+        for (int k = 0; k < 3; ++k)
+            eta[k] = sp == 0 ? mu_eta[k] : (sp <= 3 ? mu_eta[k] + sc[k * 3 + (sp - 1)] : mu_eta[k] - sc[k * 3 + (sp - 4)]);
+        for (int i = tid; i < M; i += nt) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += St[i * 3 + k] * (eta[k] - mu_eta[k]);
+            vg[i] = mu_g[i] + s;
+        }
+        __syncthreads();
+        if (tid == 0) { double s = 0; for (int i = 0; i < M; ++i) s += Jt[i] * vg[i]; sc[20] = s; }
+        __syncthreads();
+        for (int i = tid; i < np_; i += nt) {
+            const double v = i < M ? vg[i] : (i < M + 3 ? eta[i - M] : sc[20]);
+            mu_pi[i] = v;
+            mu_p[i] += w * v;
+        }
+        __syncthreads();
+        for (int e = tid; e < np_ * np_; e += nt) {
+            const int i = e / np_, j = e - i * np_;
+            double cpi = 0;
+            if (i < M && j < M) cpi = Cgp[i * M + j];
+            else if (i < M && j == M + 3) cpi = cj[i];
+            else if (i == M + 3 && j < M) cpi = JC[j];
+            else if (i == M + 3 && j == M + 3) cpi = sc[19] + sc[18];
+            C_p[e] += w * ((mu_pi[i] - mu_p[i]) * (mu_pi[j] - mu_p[j]) + cpi);
+        }
+        __syncthreads();
+    }
+    // ---- update step: o = [sigma_n, g_t] (rows M+2, M+3), u = [g, L, sigma_f]
+    const int o0 = M + 2, o1 = M + 3;
+    const double mo0 = mu_p[o0], mo1 = mu_p[o1];
+    const double Co00 = C_p[o0 * np_ + o0], Co01 = C_p[o0 * np_ + o1], Co10 = C_p[o1 * np_ + o0], Co11 = C_p[o1 * np_ + o1];
+    const double Cy = Co11 + Co00 + mo0 * mo0;
+    const double G0 = Co01 / Cy, G1 = Co11 / Cy;
+    const double me0 = mo0 + G0 * (yt - mo1), me1 = mo1 + G1 * (yt - mo1);
+    const double Ce00 = Co00 - G0 * Cy * G0, Ce01 = Co01 - G0 * Cy * G1, Ce10 = Co10 - G1 * Cy * G0, Ce11 = Co11 - G1 * Cy * G1;
+    const double det = Co00 * Co11 - Co01 * Co10;
+    const double Ci00 = Co11 / det, Ci01 = -Co01 / det, Ci10 = -Co10 / det, Ci11 = Co00 / det;
+    for (int i = tid; i < nu_; i += nt) {
+        const double c0 = C_p[o0 * np_ + i], c1 = C_p[o1 * np_ + i];
+        Lt[i * 2] = c0 * Ci00 + c1 * Ci10;
+        Lt[i * 2 + 1] = c0 * Ci01 + c1 * Ci11;
+    }
+    __syncthreads();
+    const double d0 = me0 - mo0, d1 = me1 - mo1;
+    const double D00 = Ce00 - Co00, D01 = Ce01 - Co01, D10 = Ce10 - Co10, D11 = Ce11 - Co11;
+    double* mu_z = a.mu_z ? a.mu_z + (size_t)model * nz : nullptr;
+    double* C_z = a.C_z ? a.C_z + (size_t)model * nz * nz : nullptr;
+    for (int i = tid; i < nz; i += nt) {
+        const double v = i < nu_ ? mu_p[i] + Lt[i * 2] * d0 + Lt[i * 2 + 1] * d1 : me0;
+        if (mu_z) mu_z[i] = v;
+        if (i < M) mu_g[i] = v; else mu_eta[i - M] = v;
+    }
+    for (int e = tid; e < nz * nz; e += nt) {
+        const int i = e / nz, j = e - i * nz;
+        double v;
+        if (i < nu_ && j < nu_) {
+            const double t0 = Lt[i * 2] * D00 + Lt[i * 2 + 1] * D10, t1 = Lt[i * 2] * D01 + Lt[i * 2 + 1] * D11;
+            v = C_p[i * np_ + j] + t0 * Lt[j * 2] + t1 * Lt[j * 2 + 1];
+        } else if (i < nu_) v = Lt[i * 2] * Ce00 + Lt[i * 2 + 1] * Ce10;
+        else if (j < nu_) v = Ce00 * Lt[j * 2] + Ce01 * Lt[j * 2 + 1];
+        else v = Ce00;
+        if (C_z) C_z[e] = v;
+        if (i < M && j < M) C_g[i * M + j] = v;
+        else if (i >= M && j >= M) C_eta[(i - M) * 3 + (j - M)] = v;
+    }
+    __syncthreads();
+    // ---- the pre-computed matrices follow the new hyper-parameters (RGP.py:476-479)
+    __threadfence_block();
+    const double Ln = mu_eta[0], sfn = mu_eta[1], snn = mu_eta[2];
+    const double iL2n = 1.0 / (Ln * Ln), sf2n = sfn * sfn;
+    for (int e = tid; e < M * 2 * M; e += nt) {
+        const int i = e / (2 * M), j = e - i * 2 * M;
+        W[e] = j < M ? rbf_k(X[i], X[j], iL2n, sf2n) + (i == j ? snn * snn : 0.0) : (j - M == i ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int rc = gj_inverse_cta(M, W, piv_sh);
+    if (rc == 0) for (int e = tid; e < M * M; e += nt) { const int i = e / M, j = e - i * M; Kxi[e] = W[i * 2 * M + M + j]; }
+    if (tid == 0 && a.status) a.status[model] = rc;
+}
+
 }  // namespace qmpc

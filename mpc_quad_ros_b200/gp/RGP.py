@@ -83,6 +83,12 @@ class RGP:
             return mean, np.sqrt(v)
         return mean
 
+    def learn(self, Xt, yt):
+        """RGP.py:332-482.  Hyper-parameter learning changes K_x / K_x_inv of this one model, which the control loop's
+        ensemble shares between vehicles; it lives on its own device object (never called from the loop, as in the
+        reference): use RGPLearner(X, y_, C, theta).learn(Xt, yt)."""
+        raise NotImplementedError("use mpc_quad_ros_b200.gp.RGP.RGPLearner for RGP.learn (RGP*)")
+
     def predict_using_y(self, X_t_star, y, cov=False, var=False, std=False, return_Jt=False):
         """RGP.py:235-300 numpy branch (mean only)"""
         assert isinstance(X_t_star, np.ndarray) and isinstance(y, np.ndarray)
@@ -100,3 +106,74 @@ class _Clone:
 
     def get_theta(self):
         return list(self.theta)
+
+
+class RGPLearner:
+    """RGP* — RGP.__init__ + RGP.learn of the reference (src/gp/RGP.py:106-157, 332-482, sigma points :485-505) for a batch
+    of independent 1-D models that share one basis grid X: joint recursive estimate of the function values at X and of
+    the hyper-parameters eta = (L, sigma_f, sigma_n) by the reference's unscented transform.  batch == 1 speaks numpy
+    like the reference ((1,) arrays in, (mu_z, C_z) out); batch > 1 takes / returns CUDA tensors with a leading model
+    dimension.  Attribute names follow the reference: mu_g_t, C_g_t, mu_eta_t, C_eta_t, K_x_inv, get_theta()."""
+
+    def __init__(self, X, y_=None, C=None, theta=[1.0, 0.1, 0.1], batch=1, device=None):
+        import ctypes as Ct
+        import torch
+        from .. import _capi
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        assert X.ndim == 1, "X must be a 1D array"
+        assert len(theta) == 3, "theta must be a list of 3 hyperparameters [L, sigma_f, sigma_n]"
+        self.X, self.batch, self.M = X, int(batch), X.shape[0]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._capi, self._torch = _capi, torch
+        self._h = Ct.c_void_p()
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        p = lambda a: a.ctypes.data_as(Ct.c_void_p)
+        _capi.check(_capi.lib().qrgpl_create(self.batch, self.M, p(X), p(th), self.device.index or 0, Ct.byref(self._h)))
+        if (y_ is not None and np.any(np.asarray(y_) != 0)) or C is not None:
+            mu = None if y_ is None else torch.as_tensor(np.broadcast_to(np.asarray(y_, dtype=np.float64), (self.batch, self.M)).copy(), device=self.device)
+            Cm = None if C is None else torch.as_tensor(np.broadcast_to(np.asarray(C, dtype=np.float64), (self.batch, self.M, self.M)).copy(), device=self.device)
+            _capi.check(_capi.lib().qrgpl_set_state(self._h, _capi.ptr(mu), _capi.ptr(Cm), None, None, None, None, _capi.stream_ptr()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._capi.lib().qrgpl_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _state(self, which):
+        torch, B, M = self._torch, self.batch, self.M
+        shapes = {"mu_g": (B, M), "C_g": (B, M, M), "mu_eta": (B, 3), "C_eta": (B, 3, 3), "Kx_inv": (B, M, M)}
+        t = torch.empty(shapes[which], dtype=torch.float64, device=self.device)
+        args = [self._capi.ptr(t) if k == which else None for k in ("mu_g", "C_g", "mu_eta", "C_eta", "Kx_inv")]
+        self._capi.check(self._capi.lib().qrgpl_get_state(self._h, *args, self._capi.stream_ptr()))
+        return t[0].cpu().numpy() if B == 1 else t
+
+    mu_g_t = property(lambda self: self._state("mu_g"))
+    C_g_t = property(lambda self: self._state("C_g"))
+    mu_eta_t = property(lambda self: self._state("mu_eta"))
+    C_eta_t = property(lambda self: self._state("C_eta"))
+    K_x_inv = property(lambda self: self._state("Kx_inv"))
+
+    def get_theta(self):
+        eta = self.mu_eta_t
+        return [float(v) for v in eta] if self.batch == 1 else eta
+
+    def status(self):
+        st = self._torch.empty(self.batch, dtype=self._torch.int32, device=self.device)
+        self._capi.check(self._capi.lib().qrgpl_get_status(self._h, self._capi.ptr(st), self._capi.stream_ptr()))
+        return st
+
+    def learn(self, Xt, yt):
+        """RGP.learn: one sample per model; returns (mu_z [M+3], C_z [M+3, M+3]) (leading model dimension if batched)"""
+        torch, B, M = self._torch, self.batch, self.M
+        if B == 1 and isinstance(Xt, np.ndarray):
+            assert Xt.shape[0] == 1 and yt.shape[0] == 1, "Only one-dimensional regression is supported"
+        xt = torch.as_tensor(np.asarray(Xt, dtype=np.float64).reshape(B) if not torch.is_tensor(Xt) else Xt.reshape(B), device=self.device).contiguous()
+        y = torch.as_tensor(np.asarray(yt, dtype=np.float64).reshape(B) if not torch.is_tensor(yt) else yt.reshape(B), device=self.device).contiguous()
+        mu_z = torch.empty((B, M + 3), dtype=torch.float64, device=self.device)
+        C_z = torch.empty((B, M + 3, M + 3), dtype=torch.float64, device=self.device)
+        self._capi.check(self._capi.lib().qrgpl_learn(self._h, self._capi.ptr(xt), self._capi.ptr(y), self._capi.ptr(mu_z),
+                                                       self._capi.ptr(C_z), self._capi.stream_ptr()))
+        return (mu_z[0].cpu().numpy(), C_z[0].cpu().numpy()) if B == 1 else (mu_z, C_z)

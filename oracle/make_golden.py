@@ -129,6 +129,32 @@ def ref_code_fixtures():
     print("reference_code", len(out), "arrays")
 
 
+def rgp_learn_fixtures():
+    """RGP.learn (RGP.py:332-482) sequences from the reference's own numpy code: inputs and the full state after every call"""
+    out = {}
+    for tag, M, theta, vmax, seed in [("m10", 10, [1.5, 0.5, 0.1], 5.0, 3), ("m20", 20, [3.0, 0.1, 0.01], 10.0, 4),
+                                      ("m7", 7, [1.0, 0.1, 0.1], 5.0, 5)]:
+        rng = np.random.default_rng(seed)
+        X = np.linspace(-vmax, vmax, M)
+        g = RGP(X, np.zeros(M), theta=theta)
+        T = 12
+        xt = rng.uniform(-vmax, vmax, T)
+        yt = -0.3 * xt - 0.01 * xt * np.abs(xt) + 0.05 * rng.standard_normal(T)
+        rec = {k: [] for k in ("mu_g", "C_g", "mu_eta", "C_eta", "Kx_inv", "mu_z", "C_z")}
+        out[f"learn_{tag}_C_g0"], out[f"learn_{tag}_Kx_inv0"] = g.C_g_t.copy(), g.K_x_inv.copy()
+        for t in range(T):
+            mu_z, C_z = g.learn(np.array([xt[t]]), np.array([yt[t]]))
+            for k, v in (("mu_g", g.mu_g_t), ("C_g", g.C_g_t), ("mu_eta", g.mu_eta_t), ("C_eta", g.C_eta_t),
+                         ("Kx_inv", g.K_x_inv), ("mu_z", mu_z), ("C_z", C_z)):
+                rec[k].append(np.array(v, dtype=np.float64))
+        out[f"learn_{tag}_X"], out[f"learn_{tag}_theta"] = X, np.array(theta, dtype=np.float64)
+        out[f"learn_{tag}_xt"], out[f"learn_{tag}_yt"] = xt, yt
+        for k, v in rec.items():
+            out[f"learn_{tag}_{k}"] = np.array(v)
+    np.savez_compressed(os.path.join(OUT, "rgp_learn.npz"), **out)
+    print("rgp_learn", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     log_fixture("traj2_v10_a10_gp0")                       # 299 steps, circle, gp0
@@ -137,3 +163,4 @@ if __name__ == "__main__":
     log_fixture("traj0_v15_a5_gp2", rgp=True)              # RGP + RK4
     log_fixture("traj2_v10_a10_gp2", steps=80, rgp=True)   # RGP stress (diverging covariance)
     ref_code_fixtures()
+    rgp_learn_fixtures()

@@ -164,6 +164,18 @@ def rgp_regress(X, theta, Kx_inv, mu, Cm, xt, yt):
     lib().orc_rgp_regress(X.shape[0], _p(_c(X)), _p(_c(theta)), _p(_c(Kx_inv)), _p(mu), _p(Cm), _d(xt), _d(yt))
 
 
+def rgp_learn(X, mu_g, C_g, mu_eta, C_eta, C_g_eta, Kx_inv, xt, yt):
+    """RGP.learn (RGP.py:332-482) for one sample; mu_g [M], C_g [M,M], mu_eta [3], C_eta [3,3], Kx_inv [M,M] are updated
+    IN PLACE (C-contiguous float64); returns (mu_z [M+3], C_z [M+3,M+3]) like the reference"""
+    M = X.shape[0]
+    mu_z, C_z = np.empty(M + 3), np.empty((M + 3, M + 3))
+    rc = lib().orc_rgp_learn(M, _p(_c(X)), _p(mu_g), _p(C_g), _p(mu_eta), _p(C_eta), _p(_c(C_g_eta)), _p(Kx_inv),
+                             _d(xt), _d(yt), _p(mu_z), _p(C_z))
+    if rc:
+        raise FloatingPointError("singular matrix in orc_rgp_learn")
+    return mu_z, C_z
+
+
 def rgp_alpha(Kx_inv, mu):
     out = np.empty(mu.shape[0])
     lib().orc_rgp_alpha(mu.shape[0], _p(_c(Kx_inv)), _p(_c(mu)), _p(out))

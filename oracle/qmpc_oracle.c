@@ -648,6 +648,158 @@ void orc_rgp_regress(int M, const double *X, const double *th, const double *Kx_
     free(kv);
 }
 
+/* ---- RGP* hyper-parameter learning: RGP.learn (reference src/gp/RGP.py:332-482) with its unscented transform
+ * (__draw_sigma_points, :485-505), restated as written, including the parts that look unintended:
+ *   - At (hence Jt) is built once at the current hyper-parameters and reused for every sigma point (:357-366, :392);
+ *   - the running mean mu_p_t of the cumulative sum is used inside the outer product of the same iteration (:403-404);
+ *   - C_g_eta_t is never assigned by learn, it keeps the value it came in with (zero after __init__, :153);
+ *   - the exp() transform of eta (:468-470) is overwritten by the plain assignment (:472-474).
+ * State of one 1-D model: X[M], mu_g[M], C_g[M*M], mu_eta[3]=(L,sigma_f,sigma_n), C_eta[9], C_g_eta[M*3], Kx_inv[M*M];
+ * all updated in place for the sample (xt, yt).  mu_z[M+3] / C_z[(M+3)^2] (the return value of learn) are optional. */
+static void sym3_sqrt(const double *A, double *S)      /* principal square root of a symmetric positive definite 3x3 */
+{
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = 0.5 * (A[i * 3 + j] + A[j * 3 + i]);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                double th = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) { double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += v[i][k] * sqrt(a[k][k]) * v[j][k];
+            S[i * 3 + j] = acc;
+        }
+}
+
+static int gj_inverse(int n, const double *A, double *Ainv)   /* Gauss-Jordan with partial pivoting */
+{
+    double *W = (double *)malloc(sizeof(double) * n * 2 * n);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { W[i * 2 * n + j] = A[i * n + j]; W[i * 2 * n + n + j] = (i == j); }
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int i = c + 1; i < n; ++i) if (fabs(W[i * 2 * n + c]) > fabs(W[piv * 2 * n + c])) piv = i;
+        if (W[piv * 2 * n + c] == 0) { free(W); return 1; }
+        if (piv != c) for (int j = 0; j < 2 * n; ++j) { double t = W[c * 2 * n + j]; W[c * 2 * n + j] = W[piv * 2 * n + j]; W[piv * 2 * n + j] = t; }
+        double d = 1.0 / W[c * 2 * n + c];
+        for (int j = 0; j < 2 * n; ++j) W[c * 2 * n + j] *= d;
+        for (int i = 0; i < n; ++i) if (i != c) {
+            double f = W[i * 2 * n + c];
+            if (f != 0) for (int j = 0; j < 2 * n; ++j) W[i * 2 * n + j] -= f * W[c * 2 * n + j];
+        }
+    }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Ainv[i * n + j] = W[i * 2 * n + n + j];
+    free(W);
+    return 0;
+}
+
+int orc_rgp_learn(int M, const double *X, double *mu_g, double *C_g, double *mu_eta, double *C_eta,
+                  const double *C_g_eta, double *Kx_inv, double xt, double yt, double *mu_z_out, double *C_z_out)
+{
+    const int ne = 3, np_ = M + 4, nu_ = M + 2, nz = M + 3;
+    const double L = mu_eta[0], sf = mu_eta[1];
+    double *buf = (double *)calloc((size_t)(4 * M + M * 3 + M * M + 2 * np_ + 2 * np_ * np_ + nz * nz + 2 * nu_), sizeof(double));
+    double *kv = buf, *Jt = kv + M, *vg = Jt + M, *JC = vg + M, *St = JC + M, *Cgp = St + M * 3;
+    double *mu_p = Cgp + M * M, *mu_pi = mu_p + np_, *C_pi = mu_pi + np_, *C_p = C_pi + np_ * np_;
+    double *C_z = C_p + np_ * np_, *Lt = C_z + nz * nz;
+    /* inference step (:357-366) */
+    for (int i = 0; i < M; ++i) kv[i] = rbf(xt, X[i], L, sf);
+    for (int j = 0; j < M; ++j) { double a = 0; for (int i = 0; i < M; ++i) a += kv[i] * Kx_inv[i * M + j]; Jt[j] = a; }
+    double jk = 0;
+    for (int j = 0; j < M; ++j) jk += Jt[j] * rbf(X[j], xt, L, sf);
+    const double Bv = rbf(xt, xt, L, sf) - jk;
+    double Cei[9];
+    if (gj_inverse(3, C_eta, Cei)) { free(buf); return 1; }
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < ne; ++j) { double a = 0; for (int k = 0; k < ne; ++k) a += C_g_eta[i * ne + k] * Cei[k * ne + j]; St[i * ne + j] = a; }
+    /* C_p_i = At [C_g - St C_g_eta^T, 0; 0, 0] At^T + C_w is the same for every sigma point (:398-399) */
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < M; ++j) { double a = 0; for (int k = 0; k < ne; ++k) a += St[i * ne + k] * C_g_eta[j * ne + k]; Cgp[i * M + j] = C_g[i * M + j] - a; }
+    for (int j = 0; j < M; ++j) { double a = 0; for (int i = 0; i < M; ++i) a += Jt[i] * Cgp[i * M + j]; JC[j] = a; }       /* Jt Cg' */
+    double *CJ = vg;                                                                                                 /* Cg' Jt^T (vg reused later) */
+    double *cj = (double *)malloc(sizeof(double) * M);
+    for (int i = 0; i < M; ++i) { double a = 0; for (int j = 0; j < M; ++j) a += Cgp[i * M + j] * Jt[j]; cj[i] = a; }
+    double jcj = 0; for (int j = 0; j < M; ++j) jcj += JC[j] * Jt[j];
+    for (int i = 0; i < M; ++i) {
+        for (int j = 0; j < M; ++j) C_pi[i * np_ + j] = Cgp[i * M + j];
+        C_pi[i * np_ + (M + 3)] = cj[i];
+        C_pi[(M + 3) * np_ + i] = JC[i];
+    }
+    C_pi[(M + 3) * np_ + (M + 3)] = jcj + Bv;
+    (void)CJ;
+    /* unscented transform (:379-404, :485-505) */
+    double S6[9], Ssq[9];
+    for (int i = 0; i < 9; ++i) S6[i] = (3.0 / (1.0 - 0.5)) * C_eta[i];
+    sym3_sqrt(S6, Ssq);
+    for (int sp = 0; sp < 7; ++sp) {
+        double eta[3], w = sp == 0 ? 0.5 : (1.0 - 0.5) / 6.0;
+        for (int k = 0; k < 3; ++k)
+            eta[k] = sp == 0 ? mu_eta[k] : (sp <= 3 ? mu_eta[k] + Ssq[k * 3 + (sp - 1)] : mu_eta[k] - Ssq[k * 3 + (sp - 4)]);
+        double jg = 0;
+        for (int i = 0; i < M; ++i) {
+            double a = 0;
+            for (int k = 0; k < ne; ++k) a += St[i * ne + k] * (eta[k] - mu_eta[k]);
+            vg[i] = mu_g[i] + a;
+            jg += Jt[i] * vg[i];
+        }
+        for (int i = 0; i < M; ++i) mu_pi[i] = vg[i];
+        for (int k = 0; k < 3; ++k) mu_pi[M + k] = eta[k];
+        mu_pi[M + 3] = jg;
+        for (int i = 0; i < np_; ++i) mu_p[i] += w * mu_pi[i];
+        for (int i = 0; i < np_; ++i)
+            for (int j = 0; j < np_; ++j)
+                C_p[i * np_ + j] += w * ((mu_pi[i] - mu_p[i]) * (mu_pi[j] - mu_p[j]) + C_pi[i * np_ + j]);
+    }
+    /* update step (:409-455): o = [sigma_n, g_t] at rows M+2, M+3; u = [g, L, sigma_f] */
+    const int o0 = M + 2, o1 = M + 3;
+    const double mo0 = mu_p[o0], mo1 = mu_p[o1];
+    const double Co00 = C_p[o0 * np_ + o0], Co01 = C_p[o0 * np_ + o1], Co10 = C_p[o1 * np_ + o0], Co11 = C_p[o1 * np_ + o1];
+    const double Cy = Co11 + Co00 + mo0 * mo0;
+    const double G0 = Co01 / Cy, G1 = Co11 / Cy;
+    const double me0 = mo0 + G0 * (yt - mo1), me1 = mo1 + G1 * (yt - mo1);
+    const double Ce00 = Co00 - G0 * Cy * G0, Ce01 = Co01 - G0 * Cy * G1, Ce10 = Co10 - G1 * Cy * G0, Ce11 = Co11 - G1 * Cy * G1;
+    const double det = Co00 * Co11 - Co01 * Co10;
+    const double Ci00 = Co11 / det, Ci01 = -Co01 / det, Ci10 = -Co10 / det, Ci11 = Co00 / det;
+    for (int i = 0; i < nu_; ++i) {                      /* Lt = C_ou^T inv(C_o) */
+        const double c0 = C_p[o0 * np_ + i], c1 = C_p[o1 * np_ + i];
+        Lt[i * 2] = c0 * Ci00 + c1 * Ci10;
+        Lt[i * 2 + 1] = c0 * Ci01 + c1 * Ci11;
+    }
+    const double d0 = me0 - mo0, d1 = me1 - mo1;
+    const double D00 = Ce00 - Co00, D01 = Ce01 - Co01, D10 = Ce10 - Co10, D11 = Ce11 - Co11;
+    double *mu_z = mu_pi;                                 /* reuse */
+    for (int i = 0; i < nu_; ++i) mu_z[i] = mu_p[i] + Lt[i * 2] * d0 + Lt[i * 2 + 1] * d1;
+    mu_z[nu_] = me0;
+    for (int i = 0; i < nu_; ++i) {
+        const double t0 = Lt[i * 2] * D00 + Lt[i * 2 + 1] * D10, t1 = Lt[i * 2] * D01 + Lt[i * 2 + 1] * D11;
+        for (int j = 0; j < nu_; ++j) C_z[i * nz + j] = C_p[i * np_ + j] + t0 * Lt[j * 2] + t1 * Lt[j * 2 + 1];
+        const double lc = Lt[i * 2] * Ce00 + Lt[i * 2 + 1] * Ce10;      /* Lt C_e h^T */
+        C_z[i * nz + nu_] = lc;
+        C_z[nu_ * nz + i] = Ce00 * Lt[i * 2] + Ce01 * Lt[i * 2 + 1];     /* h C_e Lt^T */
+    }
+    C_z[nu_ * nz + nu_] = Ce00;
+    /* write back (:459-479) */
+    for (int i = 0; i < M; ++i) { mu_g[i] = mu_z[i]; for (int j = 0; j < M; ++j) C_g[i * M + j] = C_z[i * nz + j]; }
+    for (int k = 0; k < 3; ++k) { mu_eta[k] = mu_z[M + k]; for (int l = 0; l < 3; ++l) C_eta[k * 3 + l] = C_z[(M + k) * nz + (M + l)]; }
+    if (mu_z_out) memcpy(mu_z_out, mu_z, sizeof(double) * nz);
+    if (C_z_out) memcpy(C_z_out, C_z, sizeof(double) * nz * nz);
+    double th[3] = {mu_eta[0], mu_eta[1], mu_eta[2]};
+    double *Kx = (double *)malloc(sizeof(double) * M * M);
+    int rc = orc_rgp_prior(M, X, th, Kx, Kx_inv);
+    free(Kx); free(cj); free(buf);
+    return rc;
+}
+
 void orc_rgp_alpha(int M, const double *Kx_inv, const double *mu, double *alpha)
 {
     for (int i = 0; i < M; ++i) { double s = 0; for (int j = 0; j < M; ++j) s += Kx_inv[i * M + j] * mu[j]; alpha[i] = s; }

@@ -448,3 +448,27 @@ def test_failed_solve_reinitialises_iterate_on_reference():
     sc2 = dict(sc); sc2["xit"], sc2["uit"] = xr, ur
     xo, uo, _, _ = oracle_solve_batch(sc2, quadp, dt, N, None)
     assert u_rel(u2, uo) < TOL_U64 and x_rel(x2, xo) < TOL_X64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["m10", "m20", "m7"])
+def test_rgp_learn_kernel_vs_reference_code(golden, tag):
+    """qrgp_learn_kernel through the C-ABI (RGPLearner) against RGP.learn of the reference's numpy code: a batch of 5
+    models fed the same 12 samples (every model must reproduce the fixture), plus the numpy-style batch-1 surface"""
+    from mpc_quad_ros_b200.gp.RGP import RGPLearner
+    g = golden("rgp_learn")
+    X, theta = g[f"learn_{tag}_X"], g[f"learn_{tag}_theta"]
+    B = 5
+    lr = RGPLearner(X, theta=list(theta), batch=B)
+    one = RGPLearner(X, np.zeros(X.shape[0]), theta=list(theta))
+    for t, (xt, yt) in enumerate(zip(g[f"learn_{tag}_xt"], g[f"learn_{tag}_yt"])):
+        mu_z, C_z = lr.learn(torch.full((B,), xt, dtype=torch.float64), torch.full((B,), yt, dtype=torch.float64))
+        assert (lr.status() == 0).all()
+        for b in (0, B - 1):
+            assert rel_err(mu_z[b].cpu().numpy(), g[f"learn_{tag}_mu_z"][t]) < TOL_RGP
+            assert rel_err(C_z[b].cpu().numpy(), g[f"learn_{tag}_C_z"][t]) < TOL_RGP
+        mz1, Cz1 = one.learn(np.array([xt]), np.array([yt]))
+        assert rel_err(mz1, g[f"learn_{tag}_mu_z"][t]) < TOL_RGP and rel_err(Cz1, g[f"learn_{tag}_C_z"][t]) < TOL_RGP
+    for name, val in (("mu_g", lr.mu_g_t), ("C_g", lr.C_g_t), ("mu_eta", lr.mu_eta_t), ("C_eta", lr.C_eta_t), ("Kx_inv", lr.K_x_inv)):
+        assert rel_err(val[B - 1].cpu().numpy(), g[f"learn_{tag}_{name}"][-1]) < TOL_RGP, name
+    assert rel_err(np.array(one.get_theta()), g[f"learn_{tag}_mu_eta"][-1]) < TOL_RGP

@@ -132,3 +132,19 @@ def test_plant_reference_code(golden, tag, quad):
         xn, nsub = orc.plant_period(quad, g[f"plant_{tag}_x"][i], g[f"plant_{tag}_u"][i], 0.05)
         assert nsub == 11          # float-accumulation quirk
         assert np.abs(xn - g[f"plant_{tag}_xnext"][i]).max() < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["m10", "m20", "m7"])
+def test_rgp_learn_matches_reference_code(golden, tag):
+    """orc_rgp_learn against RGP.learn of the reference's own numpy code (RGP.py:332-482), 12 consecutive calls:
+    return value (mu_z, C_z) and the whole state (g, eta, their covariances, the re-computed K_x^-1)"""
+    g = golden("rgp_learn")
+    X, theta = g[f"learn_{tag}_X"], g[f"learn_{tag}_theta"]
+    M = X.shape[0]
+    mu_g, C_g = np.zeros(M), np.ascontiguousarray(g[f"learn_{tag}_C_g0"].copy())
+    mu_eta, C_eta, C_g_eta = theta.copy(), np.eye(3), np.zeros((M, 3))
+    Kxi = np.ascontiguousarray(g[f"learn_{tag}_Kx_inv0"].copy())
+    for t, (xt, yt) in enumerate(zip(g[f"learn_{tag}_xt"], g[f"learn_{tag}_yt"])):
+        mu_z, C_z = orc.rgp_learn(X, mu_g, C_g, mu_eta, C_eta, C_g_eta, Kxi, xt, yt)
+        for name, val in (("mu_z", mu_z), ("C_z", C_z), ("mu_g", mu_g), ("C_g", C_g), ("mu_eta", mu_eta), ("C_eta", C_eta), ("Kx_inv", Kxi)):
+            assert rel_err(val, g[f"learn_{tag}_{name}"][t]) < 1e-11, (tag, t, name)
