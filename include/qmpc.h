@@ -50,7 +50,7 @@ typedef struct {
     int precision;       /* 64: fp64 solver (default) ; 32: fp32 Riccati/IPM (RGP stays fp64)        */
     int device;          /* CUDA device ordinal                                                       */
     int ipm_max_iter;    /* <=0 -> 50                                                                  */
-    int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 10, <0 -> off (pure IPM)     */
+    int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 20, <0 -> off (pure IPM)     */
     int warm_start_rounds; /* refinement rounds tried first from the previous solve's active set: 0 -> 6, <0 -> off */
     double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32): complementarity target of the pure IPM     */
     double ipm_mu_switch; /* <=0 -> 1e-6 (fp64) / 1e-4 (fp32): the IPM hands over to the refinement below this */
@@ -144,6 +144,8 @@ const double *qrgp_mu_device(qrgp_handle_t g);
 int qrgp_predict(qrgp_handle_t g, int m, const double *xs, double *mean, double *var, void *stream);
 /* RGP.predict_using_y numpy branch (RGP.py:264-300): xs [B][3][m], y [B][3][M] -> mean [B][3][m] */
 int qrgp_predict_using_y(qrgp_handle_t g, int m, const double *xs, const double *y, double *mean, void *stream);
+/* RGP.predict(cov=True, return_Jt=True) (RGP.py:195-229): gains Jt [B][3][m][M] and full posterior covariance [B][3][m][m] */
+int qrgp_predict_cov(qrgp_handle_t g, int m, const double *xs, double *Jt, double *cov, void *stream);
 
 /* ---- shared-swarm mode (BASELINE config 3): ONE RGP for all vehicles on all GPUs.
  * Each rank accumulates the information-form contributions of its vehicles,

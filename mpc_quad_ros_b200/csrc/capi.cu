@@ -285,6 +285,8 @@ static int solve_impl(qmpc_solver* h, void* stream)
     ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
     ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters; ia.rounds = h->rounds; ia.act = h->act;
     ia.timeline = h->timeline;
+    static const int final_rollout = getenv("QMPC_FINAL_ROLLOUT") ? atoi(getenv("QMPC_FINAL_ROLLOUT")) : 0;
+    ia.final_rollout = final_rollout;
     // QMPC_IPM_SMEM_PAD (bytes per CTA, tuning only): trades resident warps for L1 capacity
     static const size_t pad = getenv("QMPC_IPM_SMEM_PAD") ? (size_t)atol(getenv("QMPC_IPM_SMEM_PAD")) : 0;
     const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real) + pad;
@@ -554,6 +556,17 @@ int qrgp_predict(qrgp_handle_t g, int m, const double* xs, double* mean, double*
 {
     if (!g || !xs || !mean || m < 1) return fail(QMPC_ERR_ARG, "bad argument");
     return predict_launch(g, m, xs, g->mu, g->C, mean, var, stream);
+}
+
+int qrgp_predict_cov(qrgp_handle_t g, int m, const double* xs, double* Jt, double* cov, void* stream)
+{
+    if (!g || !xs || !Jt || !cov || m < 1) return fail(QMPC_ERR_ARG, "bad argument");
+    RgpCovArgs a;
+    a.B = g->B; a.M = g->M; a.m = m; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.C = g->C; a.xs = xs; a.Jt = Jt; a.cov = cov;
+    const size_t smem = (size_t)RGP_WARPS * g->M * 8;
+    qrgp_predict_cov_kernel<RGP_WARPS><<<cdiv((long long)g->B * 3, RGP_WARPS), RGP_WARPS * 32, smem, S(stream)>>>(a);
+    LAUNCH_CHECK();
+    return QMPC_OK;
 }
 
 int qrgp_predict_using_y(qrgp_handle_t g, int m, const double* xs, const double* y, double* mean, void* stream)

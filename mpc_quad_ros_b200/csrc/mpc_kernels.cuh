@@ -130,6 +130,7 @@ struct IpmArgs {
     int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
     int bail_round;                // rounds (0-based) from which a non-contracting change count ends the attempt (default 2)
     int bail_changed;              // a round that still moves more inputs than this ends the attempt at once (default: never)
+    int final_rollout;             // 1: always roll the horizon out at the end (A/B knob)
     int smem_per_warp;             // reals
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
@@ -549,7 +550,9 @@ struct WarpCtx {
     // Primal-dual active-set rounds from the active set in fx.  Each round solves the LQR with the active inputs
     // pinned (one factorisation + one forward sweep) and checks the multipliers with an adjoint sweep.
     // Returns true when the active set is self-consistent: usol then holds the exact minimiser of the box-QP.
-    __device__ bool refine_rounds(real lb, real ub, int max_rounds, int& rounds)
+    // may_bail: give up early when the change count stops contracting (warm start only: the IPM is the fall-back there;
+    // after the IPM the rounds run to max_rounds, because giving up means an IPM-accurate instead of an exact answer)
+    __device__ bool refine_rounds(real lb, real ub, int max_rounds, int& rounds, bool may_bail)
     {
         int prev_changed = 1 << 30;
         for (int round = 0; round < max_rounds; ++round) {
@@ -571,8 +574,8 @@ struct WarpCtx {
             }
             changed = warp_sum(changed);
             if (!changed) return true;
-            if (round >= a.bail_round && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
-            if (round >= 1 && changed > a.bail_changed) return false;
+            if (may_bail && round >= a.bail_round && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
+            if (may_bail && round >= 1 && changed > a.bail_changed) return false;
             prev_changed = changed;
         }
         return false;
@@ -723,7 +726,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         int known = 1;
         for (int e = lane; e < E; e += 32) { const unsigned char f = act[e]; if (f > 2) known = 0; c.fx[e] = real(f <= 2 ? f : 0); }
         known = -warp_max(-known);
-        if (known && c.refine_rounds(lb, ub, a.warm_rounds, rounds)) { exact = true; status = QMPC_STATUS_OK_; }
+        if (known && c.refine_rounds(lb, ub, a.warm_rounds, rounds, true)) { exact = true; status = QMPC_STATUS_OK_; }
     }
     if (!exact && a.hard_count) {
         if (lane == 0) a.hard_list[atomicAdd(a.hard_count, 1)] = ocp;
@@ -758,11 +761,11 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
             const real mu = warp_sum(s) * inv2E;
             if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
-            if (mu < target && resfac < real(1e-3)) {
+            if (mu < target && resfac < (refine ? real(1e-3) : real(1e-9))) {
                 if (refine) {
                     for (int e = lane; e < E; e += 32)
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
-                    if (c.refine_rounds(lb, ub, a.max_refine, rounds)) { status = QMPC_STATUS_OK_; exact = true; break; }
+                    if (c.refine_rounds(lb, ub, a.max_refine, rounds, false)) { status = QMPC_STATUS_OK_; exact = true; break; }
                     refine = false; target = a.mu_tol;       // inconsistent active set: resume the IPM to the tight tolerance
                     if (mu < target) { status = QMPC_STATUS_OK_; break; }
                 } else { status = QMPC_STATUS_OK_; break; }
@@ -874,7 +877,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     for (int e = lane; e < E; e += 32) c.usol[e] = c.ucur[e] - c.ubar[e];
     __syncwarp();
     real cost = 0;
-    if (exact) {
+    if (exact && !a.final_rollout) {
         // the pinned forward sweep of the last active-set round already holds the state increments of this solution
         // (xtr): add them and evaluate the objective element-wise instead of rolling the horizon out once more
         for (int idx = lane; idx < (N + 1) * NX; idx += 32) {

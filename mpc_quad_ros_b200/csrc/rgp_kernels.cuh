@@ -177,6 +177,59 @@ __global__ void __launch_bounds__(WARPS * 32) qrgp_predict_kernel(RgpPredArgs a)
     }
 }
 
+// RGP.predict(cov=True, return_Jt=True) (RGP.py:195-229): gain rows Jt [m][M] and the full posterior covariance
+//   C_p = K(X*,X*) - Jt K(X,X*) + Jt C_g Jt^T   [m][m]   per (vehicle, axis).  One warp per model; off the control path.
+struct RgpCovArgs {
+    int B, M, m;
+    const double* X; const double* theta; const double* Kx_inv;
+    const double* C;       // [B][3][M][M]
+    const double* xs;      // [B][3][m]
+    double* Jt;            // [B][3][m][M]   (output, also the workspace of the covariance pass)
+    double* cov;           // [B][3][m][m]
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) qrgp_predict_cov_kernel(RgpCovArgs a)
+{
+    QMPC_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int model = blockIdx.x * WARPS + warp;
+    if (model >= a.B * 3) return;
+    const int M = a.M, m = a.m, d = model % 3;
+    double* kv = reinterpret_cast<double*>(smem_raw) + (size_t)warp * M;
+    const double L = a.theta[3 * d], sf = a.theta[3 * d + 1];
+    const double iL2 = 1.0 / (L * L), sf2 = sf * sf;
+    const double* X = a.X + d * M;
+    const double* Ki = a.Kx_inv + (size_t)d * M * M;
+    const double* Cm = a.C + (size_t)model * M * M;
+    const double* xs = a.xs + (size_t)model * m;
+    double* Jt = a.Jt + (size_t)model * m * M;
+    for (int q = 0; q < m; ++q) {
+        __syncwarp();
+        for (int i = lane; i < M; i += 32) kv[i] = rbf_k(xs[q], X[i], iL2, sf2);
+        __syncwarp();
+        for (int j = lane; j < M; j += 32) {
+            double s = 0;
+            for (int i = 0; i < M; ++i) s += kv[i] * __ldg(Ki + (size_t)i * M + j);
+            Jt[(size_t)q * M + j] = s;
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < m * m; e += 32) {
+        const int q = e / m, r = e - q * m;
+        const double* Jq = Jt + (size_t)q * M;
+        const double* Jr = Jt + (size_t)r * M;
+        double jk = 0, jcj = 0;
+        for (int i = 0; i < M; ++i) {
+            jk += Jq[i] * rbf_k(X[i], xs[r], iL2, sf2);
+            double t = 0;
+            for (int j = 0; j < M; ++j) t += Cm[(size_t)i * M + j] * Jr[j];
+            jcj += Jq[i] * t;
+        }
+        a.cov[(size_t)model * m * m + e] = rbf_k(xs[q], xs[r], iL2, sf2) - jk + jcj;
+    }
+}
+
 // ------------------------------------------------------------------ shared-swarm (information form)
 
 struct RgpSharedArgs {

@@ -205,6 +205,21 @@ class GPEnsemble:
         mean, var = self.predict_tensor(self._queries(list(q)), want_var)
         return mean[0, d].cpu().numpy(), (var[0, d].cpu().numpy() if want_var else None)
 
+    def predict_cov_tensor(self, xs):
+        """gains Jt [B,3,m,M] and full posterior covariance [B,3,m,m] at the queries xs [B,3,m]"""
+        xs = xs.contiguous()
+        B, _, m = xs.shape
+        Jt = torch.empty((B, 3, m, self.M), dtype=torch.float64, device=self.device)
+        cov = torch.empty((B, 3, m, m), dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib().qrgp_predict_cov(self._h, m, _capi.ptr(xs), _capi.ptr(Jt), _capi.ptr(cov), _capi.stream_ptr()))
+        return Jt, cov
+
+    def _predict_cov_axis(self, d, xs):
+        q = np.zeros((3, xs.shape[0]))
+        q[d] = xs
+        Jt, cov = self.predict_cov_tensor(self._queries(list(q)))
+        return Jt[0, d].cpu().numpy(), cov[0, d].cpu().numpy()
+
     def _predict_using_y_axis(self, d, xs, y):
         q = np.zeros((3, xs.shape[0]))
         q[d] = xs

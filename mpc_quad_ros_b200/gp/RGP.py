@@ -74,8 +74,13 @@ class RGP:
     def predict(self, X_t_star, cov=False, var=False, std=False, return_Jt=False):
         """RGP.py:168-229 numpy branch: posterior mean (and var / std) at the query points"""
         assert isinstance(X_t_star, np.ndarray) and X_t_star.ndim == 1
-        if cov or return_Jt:
-            raise NotImplementedError("full covariance / Jt outputs are internal to regress on the GPU path")
+        if cov or return_Jt:           # same precedence and return shapes as the reference (:212-229)
+            mean, _ = self._ens._predict_axis(self._axis, X_t_star, want_var=False)
+            Jt, C_p = self._ens._predict_cov_axis(self._axis, X_t_star)
+            out = (mean, C_p) if cov else ((mean, np.diag(C_p)) if var else ((mean, np.sqrt(np.diag(C_p))) if std else (mean,)))
+            if return_Jt:
+                out = out + (Jt,)
+            return out if len(out) > 1 else out[0]
         mean, v = self._ens._predict_axis(self._axis, X_t_star, want_var=(var or std))
         if var:
             return mean, v

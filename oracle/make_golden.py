@@ -155,6 +155,24 @@ def rgp_learn_fixtures():
     print("rgp_learn", len(out), "arrays")
 
 
+def rgp_predict_cov_fixtures():
+    """RGP.predict(cov=True, return_Jt=True) (RGP.py:195-229) of the reference's numpy code after 25 regress calls"""
+    out = {}
+    rng = np.random.default_rng(77)
+    for tag, M, vmax, theta in [("m20", 20, 10.0, [3.0, 0.1, 0.01]), ("m7", 7, 5.0, [1.0, 0.1, 0.1])]:
+        g = RGP(np.linspace(-vmax, vmax, M), np.zeros(M), theta=theta)
+        xt = rng.uniform(-vmax, vmax, 25)
+        yt = -0.3 * xt + 0.05 * rng.standard_normal(25)
+        for t in range(25):
+            g.regress(np.array([xt[t]]), np.array([yt[t]]))
+        xs = np.linspace(-vmax * 1.1, vmax * 1.1, 9)
+        mu, C_p, Jt = g.predict(xs, cov=True, return_Jt=True)
+        out[f"pc_{tag}_X"], out[f"pc_{tag}_theta"], out[f"pc_{tag}_xt"], out[f"pc_{tag}_yt"] = g.X, np.array(theta), xt, yt
+        out[f"pc_{tag}_xs"], out[f"pc_{tag}_mean"], out[f"pc_{tag}_cov"], out[f"pc_{tag}_Jt"] = xs, mu, C_p, Jt
+    np.savez_compressed(os.path.join(OUT, "rgp_predict_cov.npz"), **out)
+    print("rgp_predict_cov", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     log_fixture("traj2_v10_a10_gp0")                       # 299 steps, circle, gp0
@@ -164,3 +182,4 @@ if __name__ == "__main__":
     log_fixture("traj2_v10_a10_gp2", steps=80, rgp=True)   # RGP stress (diverging covariance)
     ref_code_fixtures()
     rgp_learn_fixtures()
+    rgp_predict_cov_fixtures()
