@@ -50,7 +50,7 @@ typedef struct {
     int precision;       /* 64: fp64 solver (default) ; 32: fp32 Riccati/IPM (RGP stays fp64)        */
     int device;          /* CUDA device ordinal                                                       */
     int ipm_max_iter;    /* <=0 -> 50                                                                  */
-    int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 20, <0 -> off (pure IPM)     */
+    int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 20 (fp32: 10), <0 -> off     */
     int warm_start_rounds; /* refinement rounds tried first from the previous solve's active set: 0 -> 6, <0 -> off */
     double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32): complementarity target of the pure IPM     */
     double ipm_mu_switch; /* <=0 -> 1e-6 (fp64) / 1e-4 (fp32): the IPM hands over to the refinement below this */

@@ -56,7 +56,9 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.mu_switch = real(c.ipm_mu_switch > 0 ? c.ipm_mu_switch : (f64 ? 1e-6 : 1e-4));
     a.lam0_scale = real(0.01); a.lam0_min = real(0.1); a.lam0_max = real(100.0);
     a.refine_gtol = real(f64 ? 1e-12 : 1e-5);
-    a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? 20 : c.refine_max_rounds);
+    a.resfac_final = real(f64 ? 1e-9 : 1e-3);
+    a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? (f64 ? 20 : 10) : c.refine_max_rounds);
+    a.post_bail = f64 ? 0 : 1;
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
     a.bail_round = 2; a.bail_changed = 1 << 20; a.final_rollout = 0;

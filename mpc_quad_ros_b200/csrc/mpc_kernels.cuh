@@ -125,12 +125,14 @@ struct IpmArgs {
     real lam0_scale, lam0_min, lam0_max;   // initial multipliers of the cold IPM: clip(scale * mean|dJ/du(centre)|, min, max)
     real mu_switch;                // complementarity at which the IPM hands over to the active-set refinement
     real refine_gtol;              // sign tolerance on the multipliers of pinned inputs
+    real resfac_final;             // an IPM-only exit also needs the initial stationarity residual reduced to this fraction
     int max_iter;
     int max_refine;                // refinement rounds after the IPM; 0 = pure IPM down to mu_tol
     int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
     int bail_round;                // rounds (0-based) from which a non-contracting change count ends the attempt (default 2)
     int bail_changed;              // a round that still moves more inputs than this ends the attempt at once (default: never)
     int final_rollout;             // 1: always roll the horizon out at the end (A/B knob)
+    int post_bail;                 // 1: the rounds after the IPM may give up early too (fp32: rounding noise can keep them busy)
     int smem_per_warp;             // reals
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
@@ -761,11 +763,11 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             for (int e = lane; e < E; e += 32) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
             const real mu = warp_sum(s) * inv2E;
             if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; break; }
-            if (mu < target && resfac < (refine ? real(1e-3) : real(1e-9))) {
+            if (mu < target && resfac < (refine ? real(1e-3) : a.resfac_final)) {
                 if (refine) {
                     for (int e = lane; e < E; e += 32)
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
-                    if (c.refine_rounds(lb, ub, a.max_refine, rounds, false)) { status = QMPC_STATUS_OK_; exact = true; break; }
+                    if (c.refine_rounds(lb, ub, a.max_refine, rounds, a.post_bail != 0)) { status = QMPC_STATUS_OK_; exact = true; break; }
                     refine = false; target = a.mu_tol;       // inconsistent active set: resume the IPM to the tight tolerance
                     if (mu < target) { status = QMPC_STATUS_OK_; break; }
                 } else { status = QMPC_STATUS_OK_; break; }

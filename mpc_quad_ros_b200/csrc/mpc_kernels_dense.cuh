@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                     changed = warp_sum(changed);
                     ++round_no;
                     if (!changed) { exact = true; status = QMPC_STATUS_OK_; next = T_DONE; }
-                    else if (--rounds_left > 0) { prev_changed = changed; next = T_FIXED; }      // after the IPM the rounds never give up early
+                    else if (--rounds_left > 0 && !(a.post_bail && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; next = T_FIXED; }   // fp64: never gives up early
                     else { refine = false; target = a.mu_tol; next = T_PRED; }
                 } else if (trip == T_PRED) {
                     DPROF(6);
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                     DN_FOR_E(e) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
                     mu = warp_sum(s) * inv2E;
                     if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; next = T_DONE; }
-                    else if (mu < target && resfac < (refine ? real(1e-3) : real(1e-9))) {
+                    else if (mu < target && resfac < (refine ? real(1e-3) : a.resfac_final)) {
                         if (refine) {
                             DN_FOR_E(e) {
                                 const real fn = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
             for (int e = j; e < E; e += 16) s += c.ll[e] * c.tl[e] + c.lu[e] * c.tu[e];
             mu = c.hsum(s) * inv2E;
             if (!rfinite(mu)) { status = QMPC_STATUS_NAN_; trip = T_DONE; }
-            else if (mu < target && resfac < (refine ? real(1e-3) : real(1e-9))) {
+            else if (mu < target && resfac < (refine ? real(1e-3) : a.resfac_final)) {
                 if (refine) {
                     for (int e = j; e < E; e += 16)
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
             changed = c.hsumi(changed);
             ++round_no;
             if (!changed) { exact = true; status = QMPC_STATUS_OK_; trip = T_DONE; }
-            else if (--rounds_left > 0 && !(!ipm_started && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; trip = T_FIXED; }
+            else if (--rounds_left > 0 && !((!ipm_started || a.post_bail) && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; trip = T_FIXED; }
             else {                                   // not settling: (re)enter the IPM
                 if (ipm_started) { refine = false; target = a.mu_tol; trip = T_PRED; }
                 else if (a.hard_count) { handed = true; trip = T_DONE; }     // screening mode: the dense kernel takes it
