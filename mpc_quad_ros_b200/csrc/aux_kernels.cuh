@@ -26,14 +26,17 @@ __global__ void set_reference_kernel(int B, int N, const double* __restrict__ x_
 // linearisation cannot use (the vehicle has usually departed from its reference).  Before the next solve the SQP
 // iterate of such a vehicle is re-initialised on the new reference (states = reference, inputs = reference inputs)
 // and its remembered active set is dropped.  The reference implementation ignores acados' status (quad_opt.py:333);
-// this only acts where its behaviour is undefined.
+// this only acts where its behaviour is undefined.  A vehicle that keeps failing (two or more solves in a row: it has
+// usually crashed) gets a bounded attempt per step (IpmArgs::max_iter_failed) until a solve succeeds again, so that it
+// cannot hold up the other vehicles of its launch every step.
 __global__ void reset_failed_kernel(int B, int N, const int* __restrict__ status, const double* __restrict__ yref,
                                     const double* __restrict__ yref_e, double* __restrict__ xit, double* __restrict__ uit,
-                                    unsigned char* __restrict__ act)
+                                    unsigned char* __restrict__ act, int* __restrict__ fail_streak)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * (N + 1)) return;
     const int b = t / (N + 1), k = t - b * (N + 1);
+    if (k == 0) fail_streak[b] = status[b] == 0 ? 0 : fail_streak[b] + 1;      // consecutive failed solves of this vehicle
     if (status[b] == 0) return;
     double* x = xit + ((size_t)b * (N + 1) + k) * NX;
     if (k < N) {

@@ -71,6 +71,7 @@ struct qmpc_solver {
     unsigned char* act = nullptr;     // [B][4N] active sets remembered for the warm start
     void *W = nullptr, *fac = nullptr;
     void *xtr = nullptr, *ws = nullptr;   // scratch of the two-OCPs-per-warp solver
+    int* fail_streak = nullptr;       // [B] consecutive failed solves per vehicle
     int* hard = nullptr;              // [B + 1] list of OCPs handed from the screening kernel to the dense kernel, then the count
     int dense_grid = 0;
     long long* timeline = nullptr;    // [B][2] per-OCP start/end stamps when enabled
@@ -127,6 +128,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     ALLOC(h->alpha, B * 3 * (M ? M : 1) * 8); ALLOC(h->xit, B * (N + 1) * NX * 8); ALLOC(h->uit, B * N * NU * 8);
     ALLOC(h->u0, B * NU * 8); ALLOC(h->cost, B * 8); ALLOC(h->status, B * 4); ALLOC(h->iters, B * 4);
     ALLOC(h->xt, B * 3 * 8); ALLOC(h->yt, B * 3 * 8); ALLOC(h->rounds, B * 4); ALLOC(h->act, B * N * NU);
+    ALLOC(h->fail_streak, B * 4);
     ALLOC(h->W, B * N * WT * h->rsz); ALLOC(h->fac, B * N * FAC * h->rsz);
     ALLOC(h->gpX, 3 * (M ? M : 1) * 8);
     ALLOC(h->xtr, B * (N + 1) * NX * h->rsz); ALLOC(h->ws, B * 5 * N * NU * h->rsz);
@@ -137,6 +139,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     CU_TRY(cudaMemset(h->u0, 0, B * NU * 8)); CU_TRY(cudaMemset(h->cost, 0, B * 8));
     CU_TRY(cudaMemset(h->status, 0, B * 4)); CU_TRY(cudaMemset(h->iters, 0, B * 4));
     CU_TRY(cudaMemset(h->rounds, 0, B * 4)); CU_TRY(cudaMemset(h->act, 255, B * N * NU));
+    CU_TRY(cudaMemset(h->fail_streak, 0, B * 4));
     if (M) CU_TRY(cudaMemcpy(h->gpX, cfg->gp_X, 3 * M * 8, cudaMemcpyHostToDevice));
     h->x0_src = h->x0; h->alpha_src = h->alpha; h->alpha_stride = 3 * (int)M;
     const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N) * 8 + 16384, smem32 = smem64 / 2 + 8192;
@@ -179,7 +182,7 @@ int qmpc_destroy(qmpc_handle_t h)
     if (!h) return QMPC_OK;
     cudaSetDevice(h->cfg.device);
     void* ps[] = {h->x0, h->yref, h->yref_e, h->alpha, h->xit, h->uit, h->u0, h->cost, h->status, h->iters,
-                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act, h->xtr, h->ws, h->timeline, h->hard};
+                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act, h->xtr, h->ws, h->timeline, h->hard, h->fail_streak};
     for (void* p : ps) if (p) cudaFree(p);
     delete h;
     return QMPC_OK;
@@ -243,6 +246,7 @@ int qmpc_set_iterate(qmpc_handle_t h, const double* x, const double* u, void* st
     int rc = copy_dd(h->xit, x, B * (N + 1) * NX * 8, stream);
     if (rc) return rc;
     CU_TRY(cudaMemsetAsync(h->status, 0, B * sizeof(int), S(stream)));      // an explicit iterate is never re-initialised
+    CU_TRY(cudaMemsetAsync(h->fail_streak, 0, B * sizeof(int), S(stream)));
     return copy_dd(h->uit, u, B * N * NU * 8, stream);
 }
 
@@ -273,7 +277,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
     }
     static const bool reset_failed = !(getenv("QMPC_RESET_ON_FAIL") && atoi(getenv("QMPC_RESET_ON_FAIL")) == 0);
     if (reset_failed) {
-        reset_failed_kernel<<<cdiv((long long)B * (N + 1), 256), 256, 0, S(stream)>>>(B, N, h->status, h->yref, h->yref_e, h->xit, h->uit, h->act);
+        reset_failed_kernel<<<cdiv((long long)B * (N + 1), 256), 256, 0, S(stream)>>>(B, N, h->status, h->yref, h->yref_e, h->xit, h->uit, h->act, h->fail_streak);
         LAUNCH_CHECK();
     }
     qmpc_linearize_kernel<real><<<cdiv((long long)B * N * 16, 128), 128, 0, S(stream)>>>(la);
@@ -285,6 +289,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
     ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
     ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters; ia.rounds = h->rounds; ia.act = h->act;
     ia.timeline = h->timeline;
+    if (reset_failed) ia.fail_streak = h->fail_streak;
     static const int final_rollout = getenv("QMPC_FINAL_ROLLOUT") ? atoi(getenv("QMPC_FINAL_ROLLOUT")) : 0;
     ia.final_rollout = final_rollout;
     // QMPC_IPM_SMEM_PAD (bytes per CTA, tuning only): trades resident warps for L1 capacity

@@ -127,6 +127,8 @@ struct IpmArgs {
     real refine_gtol;              // sign tolerance on the multipliers of pinned inputs
     real resfac_final;             // an IPM-only exit also needs the initial stationarity residual reduced to this fraction
     int max_iter;
+    int max_iter_failed;           // iteration limit of a vehicle whose last two solves failed (fail_streak >= 2)
+    const int* fail_streak;        // [B] consecutive failed solves, or null
     int max_refine;                // refinement rounds after the IPM; 0 = pure IPM down to mu_tol
     int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
     int bail_round;                // rounds (0-based) from which a non-contracting change count ends the attempt (default 2)
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
                     if (mu < target) { status = QMPC_STATUS_OK_; break; }
                 } else { status = QMPC_STATUS_OK_; break; }
             }
-            if (it >= a.max_iter) break;
+            if (it >= ((a.fail_streak && a.fail_streak[ocp] >= 2) ? a.max_iter_failed : a.max_iter)) break;
             // predictor
             for (int e = lane; e < E; e += 32) {
                 const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];

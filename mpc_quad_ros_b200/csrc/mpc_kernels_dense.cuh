@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                             }
                             next = T_FIXED; rounds_left = a.max_refine; prev_changed = 1 << 30; round_no = 0;
                         } else { status = QMPC_STATUS_OK_; next = T_DONE; }
-                    } else if (it >= a.max_iter) next = T_DONE;
+                    } else if (it >= ((a.fail_streak && a.fail_streak[ocp] >= 2) ? a.max_iter_failed : a.max_iter)) next = T_DONE;
                 }
                 __syncwarp();
                 if (lane == 0) ctl[0] = next;

@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
                     trip = T_FIXED; rounds_left = a.max_refine; prev_changed = 1 << 30; round_no = 0;
                 } else { status = QMPC_STATUS_OK_; trip = T_DONE; }
-            } else if (it >= a.max_iter) trip = T_DONE;
+            } else if (it >= ((a.fail_streak && a.fail_streak[ocp] >= 2) ? a.max_iter_failed : a.max_iter)) trip = T_DONE;
             if (trip == T_PRED) {
                 for (int e = j; e < E; e += 16) {
                     const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];

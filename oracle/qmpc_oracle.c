@@ -938,7 +938,7 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
             }
             const double *yref_e = chunk + (N - 1) * NX;
             if (use_gp) for (int d = 0; d < 3; ++d) orc_rgp_alpha(M, Kx_inv + d * M * M, mub + d * M, alpha + d * M);
-            if (have_pred[b] == 2) {      /* previous solve failed: restart the SQP iterate on the new reference */
+            if (have_pred[b] >= 2) {      /* previous solve failed: restart the SQP iterate on the new reference */
                 for (int k = 0; k < N; ++k) {
                     memcpy(xi + k * NX, chunk + k * NX, sizeof(double) * NX);
                     for (int a = 0; a < NU; ++a) ui[k * NU + a] = u_ref;
@@ -948,7 +948,9 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
             double xnow[NX], cost, kkt; int iters;
             memcpy(xnow, xb, sizeof(xnow));
             int st = orc_rti_step(quad, dt, N, use_gp ? M : 0, gpX, gpth, use_gp ? alpha : NULL, Wd, Wed, 0.0, 1.0,
-                                  xnow, yref, yref_e, xi, ui, &cost, &iters, &kkt, mu_tol, max_iter, do_polish, NULL);
+                                  xnow, yref, yref_e, xi, ui, &cost, &iters, &kkt, mu_tol,
+                                  (have_pred[b] >= 3 && max_iter > 20) ? 20 : max_iter,   /* two failures in a row: bounded attempt */
+                                  do_polish, NULL);
             if (st > 1) bad += 1;
             double u0[NU], xpred[NX];
             memcpy(u0, ui, sizeof(u0));
@@ -966,7 +968,7 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
                     orc_rgp_regress(M, gpX + d * M, gpth + 3 * d, Kx_inv + d * M * M, mub + d * M, Cb + d * M * M, vb[d], ad[d]);
             }
             memcpy(xpred_prev + (size_t)b * NX, xpred, sizeof(xpred));
-            have_pred[b] = st > 1 ? 2 : 1;
+            have_pred[b] = st > 1 ? (have_pred[b] >= 2 ? have_pred[b] + 1 : 2) : 1;   /* 1 ok, 1 + number of consecutive failures */
         }
         free(yref); free(chunk); free(alpha);
     }
