@@ -53,7 +53,7 @@ typedef struct {
     int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 20 (fp32: 10), <0 -> off     */
     int warm_start_rounds; /* refinement rounds tried first from the previous solve's active set: 0 -> 6, <0 -> off */
     double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32): complementarity target of the pure IPM     */
-    double ipm_mu_switch; /* <=0 -> 1e-6 (fp64) / 1e-4 (fp32): the IPM hands over to the refinement below this */
+    double ipm_mu_switch; /* <=0 -> 1e-4: the IPM hands over to the active-set refinement below this          */
     double t_horizon;    /* tf ; dt = t_horizon / n_nodes (quad_opt.py:43)                            */
     double quad[20];     /* mass, max_thrust, J[3], x_f[4], y_f[4], z_l_tau[4], g[3]                  */
     double w_diag[17];   /* LINEAR_LS stage weights diag(W) (quad_opt.py:122-129); scaled by dt inside */

@@ -55,7 +55,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.max_iter = c.ipm_max_iter > 0 ? c.ipm_max_iter : 50;
     a.max_iter_failed = a.max_iter < 20 ? a.max_iter : 20;
     a.fail_streak = nullptr;
-    a.mu_switch = real(c.ipm_mu_switch > 0 ? c.ipm_mu_switch : (f64 ? 1e-6 : 1e-4));
+    a.mu_switch = real(c.ipm_mu_switch > 0 ? c.ipm_mu_switch : 1e-4);
     a.lam0_scale = real(0.01); a.lam0_min = real(0.1); a.lam0_max = real(100.0);
     a.refine_gtol = real(f64 ? 1e-12 : 1e-5);
     a.resfac_final = real(f64 ? 1e-9 : 1e-3);

@@ -757,6 +757,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             c.ll[e] = lam0; c.lu[e] = lam0;
         }
         real resfac = 1;                  // fraction of the initial stationarity residual still present
+        int attempts = 0;                 // hand-overs to the active-set rounds so far
         bool refine = a.max_refine > 0;
         real target = refine ? a.mu_switch : a.mu_tol;
         const real inv2E = real(1) / real(2 * E);
@@ -770,8 +771,10 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
                     for (int e = lane; e < E; e += 32)
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
                     if (c.refine_rounds(lb, ub, a.max_refine, rounds, a.post_bail != 0)) { status = QMPC_STATUS_OK_; exact = true; break; }
-                    refine = false; target = a.mu_tol;       // inconsistent active set: resume the IPM to the tight tolerance
-                    if (mu < target) { status = QMPC_STATUS_OK_; break; }
+                    // inconsistent active set: one more attempt from a 100x sharper IPM point, then the IPM alone to mu_tol
+                    if (++attempts < 2) target *= real(1e-2);
+                    else { refine = false; target = a.mu_tol; }
+                    if (!refine && mu < target) { status = QMPC_STATUS_OK_; break; }
                 } else { status = QMPC_STATUS_OK_; break; }
             }
             if (it >= ((a.fail_streak && a.fail_streak[ocp] >= 2) ? a.max_iter_failed : a.max_iter)) break;

@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
         // ---- box-QP: warp 0 drives (element-wise work, triangular solves, decisions); the CTA factors and multiplies
         int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
         bool exact = false, refine = a.max_refine > 0;
-        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0;
+        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, attempts = 0;
         real target = refine ? a.mu_switch : a.mu_tol, mu = 0, resfac = 1;
         const real inv2E = real(1) / real(2 * E);
         int trip = T_GRAD;
@@ -504,7 +504,10 @@ __global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<rea
                     ++round_no;
                     if (!changed) { exact = true; status = QMPC_STATUS_OK_; next = T_DONE; }
                     else if (--rounds_left > 0 && !(a.post_bail && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; next = T_FIXED; }   // fp64: never gives up early
-                    else { refine = false; target = a.mu_tol; next = T_PRED; }
+                    else {      // one more attempt from a 100x sharper IPM point, then the IPM alone
+                        if (++attempts < 2) target *= real(1e-2); else { refine = false; target = a.mu_tol; }
+                        next = T_PRED;
+                    }
                 } else if (trip == T_PRED) {
                     DPROF(6);
                     c.solve(c.rt, c.usol, true);

@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
     enum { T_FIXED, T_ADJ, T_PRED, T_CORR, T_GFWD, T_GADJ, T_DONE };
     int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
     bool exact = false, refine = a.max_refine > 0, ipm_started = false, handed = false;
-    int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, trip = T_GFWD, cpass = 0;
+    int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, trip = T_GFWD, cpass = 0, attempts = 0;
     real target = refine ? a.mu_switch : a.mu_tol, mu = 0, sigma = 0, so = 1, resfac = 1;
     const real inv2E = real(1) / real(2 * E);
     if (a.warm_rounds > 0) {
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM2_MIN_WARPS / WARPS) qmpc_
             if (!changed) { exact = true; status = QMPC_STATUS_OK_; trip = T_DONE; }
             else if (--rounds_left > 0 && !((!ipm_started || a.post_bail) && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; trip = T_FIXED; }
             else {                                   // not settling: (re)enter the IPM
-                if (ipm_started) { refine = false; target = a.mu_tol; trip = T_PRED; }
+                if (ipm_started) { if (++attempts < 2) target *= real(1e-2); else { refine = false; target = a.mu_tol; } trip = T_PRED; }
                 else if (a.hard_count) { handed = true; trip = T_DONE; }     // screening mode: the dense kernel takes it
                 else trip = T_GFWD;
             }
