@@ -560,12 +560,17 @@ struct WarpCtx {
     {
         int prev_changed = 1 << 30;
         for (int round = 0; round < max_rounds; ++round) {
-            for (int e = lane; e < E; e += 32) fv[e] = fx[e] == real(1) ? lb - ubar[e] : (fx[e] == real(2) ? ub - ubar[e] : real(0));
+            int pinned = 0;
+            for (int e = lane; e < E; e += 32) {
+                fv[e] = fx[e] == real(1) ? lb - ubar[e] : (fx[e] == real(2) ? ub - ubar[e] : real(0));
+                pinned += fx[e] != real(0);
+            }
+            pinned = warp_sum(pinned);
             __syncwarp();
             backward_full<true>();
             forward<0, true>();
             __syncwarp();
-            backward_adjoint();
+            if (pinned) backward_adjoint();       // multipliers are only looked at for pinned inputs
             __syncwarp();
             ++rounds;
             int changed = 0;
