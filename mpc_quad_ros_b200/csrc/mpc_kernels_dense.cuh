@@ -282,8 +282,12 @@ struct DenseCtx {
 // element loop of warp 0: e = lane, lane + 32, lane + 64 (E <= 96), unrolled so the three elements overlap
 #define DN_FOR_E(e) _Pragma("unroll") for (int e##_m = 0; e##_m < 3; ++e##_m) for (int e = lane + 32 * e##_m; e < E; e = E)
 
+#ifndef QMPC_DENSE_MIN_CTAS
+#define QMPC_DENSE_MIN_CTAS 2       // register budget: 2 -> 128 registers per thread
+#endif
+
 template <typename real>
-__global__ void __launch_bounds__(DN_THREADS, 2) qmpc_dense_kernel(DenseArgs<real> da)
+__global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_kernel(DenseArgs<real> da)
 {
     QMPC_DYN_SMEM(smem_raw);
     const IpmArgs<real>& a = da.b;
