@@ -303,13 +303,15 @@ static int solve_impl(qmpc_solver* h, void* stream)
         qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
     } else if (h->variant == 2 || h->variant == 3) {
         // screening: warm-started active-set rounds in a Riccati kernel; whatever does not settle goes to the dense kernel
-        static const int screen_rounds = getenv("QMPC_SCREEN_ROUNDS") ? atoi(getenv("QMPC_SCREEN_ROUNDS")) : 6;
+        static const int screen_rounds = getenv("QMPC_SCREEN_ROUNDS") ? atoi(getenv("QMPC_SCREEN_ROUNDS")) : 3;
         CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
         ia.hard_list = h->hard; ia.hard_count = h->hard + B;
         if (ia.warm_rounds > screen_rounds) ia.warm_rounds = screen_rounds;
         static const int bail_round = getenv("QMPC_BAIL_ROUND") ? atoi(getenv("QMPC_BAIL_ROUND")) : 2;
         static const int bail_changed = getenv("QMPC_BAIL_CHANGED") ? atoi(getenv("QMPC_BAIL_CHANGED")) : (1 << 20);
         ia.bail_round = bail_round; ia.bail_changed = bail_changed;
+        static const int dense_warm = getenv("QMPC_DENSE_WARM_ROUNDS") ? atoi(getenv("QMPC_DENSE_WARM_ROUNDS")) : 8;
+        ia.dense_warm_rounds = dense_warm;
         if (h->variant == 3) {
             Ipm2Args<real> i2;
             i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N);

@@ -63,7 +63,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.post_bail = f64 ? 0 : 1;
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
-    a.bail_round = 2; a.bail_changed = 1 << 20; a.final_rollout = 0;
+    a.bail_round = 2; a.bail_changed = 1 << 20; a.final_rollout = 0; a.dense_warm_rounds = 0;
     a.timeline = nullptr; a.hard_list = nullptr; a.hard_count = nullptr;
 }
 

@@ -131,6 +131,7 @@ struct IpmArgs {
     const int* fail_streak;        // [B] consecutive failed solves, or null
     int max_refine;                // refinement rounds after the IPM; 0 = pure IPM down to mu_tol
     int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
+    int dense_warm_rounds;         // dense kernel: active-set rounds from the handed-over guess before the IPM; 0 = IPM first
     int bail_round;                // rounds (0-based) from which a non-contracting change count ends the attempt (default 2)
     int bail_changed;              // a round that still moves more inputs than this ends the attempt at once (default: never)
     int final_rollout;             // 1: always roll the horizon out at the end (A/B knob)
@@ -738,7 +739,14 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         if (known && c.refine_rounds(lb, ub, a.warm_rounds, rounds, true)) { exact = true; status = QMPC_STATUS_OK_; }
     }
     if (!exact && a.hard_count) {
-        if (lane == 0) a.hard_list[atomicAdd(a.hard_count, 1)] = ocp;
+        // screening mode: hand the OCP to the dense kernel together with the active-set guess the rounds ended on
+        if (a.warm_rounds > 0) {
+            bool was_known = true;
+            for (int e = lane; e < E; e += 32) was_known = was_known && act[e] <= 2;
+            was_known = warp_max(int(!was_known)) == 0;
+            if (was_known) for (int e = lane; e < E; e += 32) act[e] = c.fx[e] == real(1) ? 1 : (c.fx[e] == real(2) ? 2 : 0);
+        }
+        if (lane == 0) { a.rounds[ocp] = rounds; a.hard_list[atomicAdd(a.hard_count, 1)] = ocp; }
         return;
     }
     // ---- 2. Mehrotra predictor-corrector IPM (cold start), handing over to the active-set refinement at mu_switch

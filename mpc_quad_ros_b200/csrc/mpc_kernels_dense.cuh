@@ -432,18 +432,28 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
 #pragma unroll
             for (int t = 0; t < 16; t += 2) st2(o + t, acc[t], acc[t + 1]);
         }
-        if (tid < E) {
-            c.f[tid] += fc;
-            c.usol[tid] = real(0.5) * (lb + ub) - c.ubar[tid];
+        if (tid < E) c.f[tid] += fc;
+        // ---- box-QP: warp 0 drives (element-wise work, triangular solves, decisions); the CTA factors and multiplies.
+        // Start: active-set rounds from the guess the screening kernel ended on (a round costs a quarter of a Riccati
+        // round here), the IPM from the box centre if there is no guess or the rounds do not settle.
+        int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
+        bool exact = false, refine = a.max_refine > 0, ipm_started = false;
+        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, attempts = 0;
+        if (warp == 0) {
+            int known = a.dense_warm_rounds > 0 && da.hard_list != nullptr;
+            DN_FOR_E(e) { const unsigned char fl = actset[e]; if (fl > 2) known = 0; c.fx[e] = real(fl <= 2 ? fl : 0); }
+            known = warp_max(int(!known)) == 0;
+            if (known) {
+                DN_FOR_E(e) c.fv[e] = c.fx[e] == real(1) ? lb - c.ubar[e] : (c.fx[e] == real(2) ? ub - c.ubar[e] : real(0));
+                rounds_left = a.dense_warm_rounds;
+                rounds = a.rounds[ocp];              // rounds already spent in the screening kernel
+            } else {
+                DN_FOR_E(e) c.usol[e] = real(0.5) * (lb + ub) - c.ubar[e];
+            }
+            if (lane == 0) ctl[0] = known ? T_FIXED : T_GRAD;
         }
-        if (tid == 0) ctl[0] = T_GRAD;
         __syncthreads();
         DPROF(0);
-
-        // ---- box-QP: warp 0 drives (element-wise work, triangular solves, decisions); the CTA factors and multiplies
-        int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
-        bool exact = false, refine = a.max_refine > 0;
-        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, attempts = 0;
         real target = refine ? a.mu_switch : a.mu_tol, mu = 0, resfac = 1;
         const real inv2E = real(1) / real(2 * E);
         int trip = T_GRAD;
@@ -487,6 +497,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                         const real u0 = real(0.5) * (lb + ub);
                         c.ucur[e] = u0; c.tl[e] = u0 - lb; c.tu[e] = ub - u0; c.ll[e] = lam0; c.lu[e] = lam0;
                     }
+                    ipm_started = true;
                     next = T_PRED;
                 } else if (trip == T_FIXED) {
                     c.solve(c.rt, c.usol, true);
@@ -507,8 +518,11 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     changed = warp_sum(changed);
                     ++round_no;
                     if (!changed) { exact = true; status = QMPC_STATUS_OK_; next = T_DONE; }
-                    else if (--rounds_left > 0 && !(a.post_bail && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; next = T_FIXED; }   // fp64: never gives up early
-                    else {      // one more attempt from a 100x sharper IPM point, then the IPM alone
+                    else if (--rounds_left > 0 && !((!ipm_started || a.post_bail) && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; next = T_FIXED; }   // after the IPM (fp64) the rounds never give up early
+                    else if (!ipm_started) {     // the warm rounds did not settle: IPM from the box centre
+                        DN_FOR_E(e) c.usol[e] = real(0.5) * (lb + ub) - c.ubar[e];
+                        next = T_GRAD;
+                    } else {      // one more attempt from a 100x sharper IPM point, then the IPM alone
                         if (++attempts < 2) target *= real(1e-2); else { refine = false; target = a.mu_tol; }
                         next = T_PRED;
                     }

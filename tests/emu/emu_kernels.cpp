@@ -32,6 +32,8 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
     } else if (variant == 2 || variant == 3) {      // screening kernel (warm-started rounds) + dense kernel for the rest
         std::vector<int> list(B), cnt(1, 0);
         ia.hard_list = list.data(); ia.hard_count = cnt.data();
+        if (getenv("QMPC_SCREEN_ROUNDS") && ia.warm_rounds > atoi(getenv("QMPC_SCREEN_ROUNDS"))) ia.warm_rounds = atoi(getenv("QMPC_SCREEN_ROUNDS"));
+        if (getenv("QMPC_DENSE_WARM_ROUNDS")) ia.dense_warm_rounds = atoi(getenv("QMPC_DENSE_WARM_ROUNDS"));
         if (variant == 2) {
             emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
                         [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });

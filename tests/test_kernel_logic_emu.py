@@ -88,3 +88,27 @@ def test_emulated_warm_start_from_previous_active_set(variant):
     r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=act.copy(), variant=variant)
     assert (r2["status"] == 0).all() and (r2["rounds"] >= 1).all()
     assert u_rel(u2, uo) < TOL[variant] and x_rel(x2, xo) < TOL[variant]
+
+
+def test_emulated_dense_kernel_continues_the_screening_rounds(monkeypatch):
+    """screening limited to one round, the dense kernel continues with active-set rounds from the handed-over guess
+    (QMPC_SCREEN_ROUNDS=1, QMPC_DENSE_WARM_ROUNDS=8) and falls back to its IPM: same exact minimiser"""
+    monkeypatch.setenv("QMPC_SCREEN_ROUNDS", "1")
+    monkeypatch.setenv("QMPC_DENSE_WARM_ROUNDS", "8")
+    B, N = 4, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(20)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=3, amp_choices=(8.0, 2.0))
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=2)
+    sc2 = dict(sc)
+    sc2["x0"] = sc["x0"] + 0.05 * np.random.default_rng(1).standard_normal(sc["x0"].shape)   # moves the active set
+    sc2["xit"], sc2["uit"] = xe.copy(), ue.copy()
+    xo, uo, _, _ = oracle_solve_batch(sc2, quad, dt, N, gp)
+    x2, u2 = xe.copy(), ue.copy()
+    r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=r1["act"].copy(), variant=2)
+    assert (r2["status"] == 0).all()
+    assert u_rel(u2, uo) < TOL[2] and x_rel(x2, xo) < TOL[2]
+    print("dense continuation: ipm iters", r2["iters"], "rounds", r2["rounds"])
