@@ -294,8 +294,8 @@ def b200_arm(a):
     achieved = ipm_flops / (ipm_ms * 1e-3) / 1e12 if ipm_ms > 0 else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of this
     # exact shape (profiles/r01_ipm_summary.txt); other shapes were not captured
-    # (screening launch 286.6 MB + dense launch 8.8 MB)
-    traffic = 295.4e6 if (B, N, M, a.precision, a.workload, a.cold) == (4096, 20, 20, 64, "random_smooth", False) else None
+    # (screening launch 273.5 MB + dense launch 20.3 MB)
+    traffic = 293.8e6 if (B, N, M, a.precision, a.workload, a.cold) == (4096, 20, 20, 64, "random_smooth", False) else None
     roofline = {"kernel": "qmpc_ipm_kernel (warm-started Riccati screening) + qmpc_dense_kernel (condensed IPM/active-set for the rest)"
                           if a.precision == 64 and N <= 21 else "qmpc_ipm_kernel",
                 "bound": "fp%d_fma" % a.precision, "achieved": achieved, "peak": peak.value,
