@@ -112,3 +112,24 @@ def test_emulated_dense_kernel_continues_the_screening_rounds(monkeypatch):
     assert (r2["status"] == 0).all()
     assert u_rel(u2, uo) < TOL[2] and x_rel(x2, xo) < TOL[2]
     print("dense continuation: ipm iters", r2["iters"], "rounds", r2["rounds"])
+
+
+@pytest.mark.parametrize("variant", [0, 2], ids=["warp_per_ocp", "screen_plus_dense"])
+def test_emulated_breakdown_is_contained(variant):
+    """a non-finite iterate in ONE vehicle: that vehicle reports status 2, keeps its iterate, holds its (clipped) previous
+    first control and forgets its active set; its neighbours (same warp / same CTA loop) are solved as if it were not there"""
+    B, N = 3, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    sc = random_ocp_batch(B, N, dt, quad, None, seed=21, amp_choices=(2.0,))
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG)
+    xo, uo, _, _ = oracle_solve_batch(sc, quad, dt, N, None)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    xe[1, 4, 8] = np.nan
+    ue[1, 0] = [0.3, 1.7, -0.2, 0.5]
+    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], None, xe, ue, variant=variant)
+    assert r["status"].tolist() == [0, 2, 0]
+    assert np.allclose(r["u0"][1], [0.3, 1.0, 0.0, 0.5]) and (r["act"][1] == 255).all()
+    assert np.isnan(xe[1, 4, 8]) and np.array_equal(ue[1, 0], [0.3, 1.7, -0.2, 0.5])       # iterate untouched
+    for b in (0, 2):
+        assert np.abs(ue[b] - uo[b]).max() < TOL[variant] and np.abs(xe[b] - xo[b]).max() < 10 * TOL[variant]
