@@ -50,7 +50,10 @@ def parse():
     ap.add_argument("--v-peak", type=float, default=15.0, help="lemniscate peak speed (m/s)")
     ap.add_argument("--warm-rounds", type=int, default=0, help="active-set rounds tried from the previous active set (0 = library default)")
     ap.add_argument("--mu-switch", type=float, default=0.0, help="IPM -> refinement hand-over complementarity (0 = library default)")
-    return ap.parse_args()
+    ap.add_argument("--solver-opts", default="", help="qmpc_config solver-policy fields for A/B runs, e.g. screen_rounds=6,bail_round=3")
+    a = ap.parse_args()
+    a.policy = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in a.solver_opts.split(",") if kv}
+    return a
 
 
 def workload_config(a, n_gpus):
@@ -211,7 +214,7 @@ def b200_arm(a):
         quad = Quadrotor3D(drag=True, batch=count, device=dev).set_hummingbird_params()
         gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=(1 if a.shared_rgp else count), device=dev) if M else None
         opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=a.precision,
-                             warm_start_rounds=(-1 if a.cold else a.warm_rounds), ipm_mu_switch=a.mu_switch)
+                             warm_start_rounds=(-1 if a.cold else a.warm_rounds), ipm_mu_switch=a.mu_switch, **a.policy)
         swarm = SharedSwarmRGP(gpe, opt) if (a.shared_rgp and M) else None
         return ClosedLoop(quad, opt, torch.as_tensor(traj_np[first:first + count]), torch.as_tensor(x0_np[first:first + count]),
                           shared_swarm=swarm)

@@ -51,7 +51,8 @@ typedef struct {
     int device;          /* CUDA device ordinal                                                       */
     int ipm_max_iter;    /* <=0 -> 50                                                                  */
     int refine_max_rounds; /* active-set refinement rounds after the IPM: 0 -> 20 (fp32: 10), <0 -> off     */
-    int warm_start_rounds; /* refinement rounds tried first from the previous solve's active set: 0 -> 6, <0 -> off */
+    int warm_start_rounds; /* refinement rounds tried first from the previous solve's active set: 0 -> 6,
+                              <0 -> off (cold IPM every step, in every kernel of the solver)                  */
     double ipm_mu_tol;   /* <=0 -> 1e-13 (fp64) / 1e-6 (fp32): complementarity target of the pure IPM     */
     double ipm_mu_switch; /* <=0 -> 1e-4: the IPM hands over to the active-set refinement below this          */
     double t_horizon;    /* tf ; dt = t_horizon / n_nodes (quad_opt.py:43)                            */
@@ -61,6 +62,19 @@ typedef struct {
     double lbu, ubu;     /* input box (quad_opt.py:142-143)                                            */
     double gp_theta[9];  /* per axis (L, sigma_f, sigma_n) (RGP.py:106)                                */
     const double *gp_X;  /* host [3][M] basis points, may be NULL when n_basis == 0                    */
+    /* ---- solver policy, per handle (every field: 0 -> library default).  The reference has no counterpart: acados
+     * cold-starts HPIPM every step and ignores its status (quad_opt.py:333, _acados_ocp.json qp_solver_warm_start 0). */
+    int solver_variant;    /* 0 -> auto: Riccati screening launch + dense condensed launch for fp64 with N <= 21, the
+                              Riccati kernel alone otherwise; 1 -> Riccati kernel alone; 2 -> screening + dense */
+    int reset_on_fail;     /* 0 -> on: a vehicle whose last solve failed (status != 0) restarts its SQP iterate on the new
+                              reference and, from the second failure in a row, gets a bounded attempt per step;
+                              <0 -> off: keep whatever the solver left, as the reference does */
+    int screen_rounds;     /* active-set rounds the screening launch tries before it hands an OCP over: 0 -> 3 */
+    int dense_warm_rounds; /* rounds the dense kernel continues from the handed-over guess before its IPM: 0 -> 8, <0 -> none */
+    int bail_round;        /* round (0-based) from which a non-contracting change count ends a warm attempt: 0 -> 2 */
+    int bail_changed;      /* a warm round that still moves more inputs than this ends the attempt: 0 -> never */
+    int final_rollout;     /* >0 -> always re-roll the horizon at the end of a solve (A/B knob): 0 -> reuse the last sweep */
+    int dense_grid;        /* persistent CTAs of the dense launch: 0 -> min(resident CTAs, max(32, B/6)) */
 } qmpc_config;
 
 const char *qmpc_last_error(void);
@@ -99,8 +113,12 @@ int qmpc_get_x(qmpc_handle_t h, double *x /*[B][N+1][13]*/, void *stream);
 int qmpc_get_u(qmpc_handle_t h, double *u /*[B][N][4]*/, void *stream);
 int qmpc_get_cost(qmpc_handle_t h, double *cost /*[B]*/, void *stream);
 int qmpc_get_status(qmpc_handle_t h, int *status /*[B]*/, int *iters /*[B]*/, void *stream);
+/* consecutive failed solves per vehicle (0 = last solve fine); all zero when reset_on_fail is off */
+int qmpc_get_fail_streak(qmpc_handle_t h, int *streak /*[B]*/, void *stream);
 /* active-set refinement rounds of the last solve (warm-start rounds + rounds after the IPM), [B] */
 int qmpc_get_refine_rounds(qmpc_handle_t h, int *rounds /*[B]*/, void *stream);
+/* OCPs the screening launch of the last solve handed to the dense launch (host value; synchronises `stream`) */
+int qmpc_get_hard_count(qmpc_handle_t h, int *count_host, void *stream);
 /* forget the active sets remembered for the warm start (the next solve starts from the cold IPM) */
 int qmpc_reset_warm_start(qmpc_handle_t h, void *stream);
 /* sum over vehicles of IPM iterations of the last solve (host value; synchronises `stream`) */

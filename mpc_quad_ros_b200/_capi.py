@@ -20,6 +20,8 @@ class QmpcConfig(C.Structure):
         ("quad", C.c_double * 20), ("w_diag", C.c_double * 17), ("we_diag", C.c_double * 13),
         ("lbu", C.c_double), ("ubu", C.c_double), ("gp_theta", C.c_double * 9),
         ("gp_X", C.POINTER(C.c_double)),
+        ("solver_variant", C.c_int), ("reset_on_fail", C.c_int), ("screen_rounds", C.c_int), ("dense_warm_rounds", C.c_int),
+        ("bail_round", C.c_int), ("bail_changed", C.c_int), ("final_rollout", C.c_int), ("dense_grid", C.c_int),
     ]
 
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -15,7 +16,6 @@
 #include "aux_kernels.cuh"
 #include "host_params.h"
 #include "mpc_kernels.cuh"
-#include "mpc_kernels_v2.cuh"
 #include "mpc_kernels_dense.cuh"
 #include "rgp_kernels.cuh"
 
@@ -53,10 +53,6 @@ inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 #define QMPC_IPM_WARPS 1      // one OCP per CTA: a finished warp frees its SM slot at once (IPM iteration counts vary)
 #endif
 constexpr int IPM_WARPS = QMPC_IPM_WARPS;
-#ifndef QMPC_IPM2_WARPS
-#define QMPC_IPM2_WARPS 2     // two-OCPs-per-warp kernel: 4 OCPs per CTA, 7 CTAs per SM (shared-memory bound)
-#endif
-constexpr int IPM2_WARPS = QMPC_IPM2_WARPS;
 constexpr int RGP_WARPS = 4;
 
 }  // namespace
@@ -70,13 +66,12 @@ struct qmpc_solver {
     int *status = nullptr, *iters = nullptr, *rounds = nullptr;
     unsigned char* act = nullptr;     // [B][4N] active sets remembered for the warm start
     void *W = nullptr, *fac = nullptr;
-    void *xtr = nullptr, *ws = nullptr;   // scratch of the two-OCPs-per-warp solver
     int* fail_streak = nullptr;       // [B] consecutive failed solves per vehicle
     int* hard = nullptr;              // [B + 1] list of OCPs handed from the screening kernel to the dense kernel, then the count
     int dense_grid = 0;
     long long* timeline = nullptr;    // [B][2] per-OCP start/end stamps when enabled
-    int variant = 2;                  // QMPC_IPM_VARIANT (A/B knob): 0 Riccati kernel alone (one OCP per warp), 1 two OCPs per warp,
-                                      // 2 (default) Riccati screening + dense kernel, 3 two-OCP screening + dense kernel
+    int variant = 2;                  // host_params.h solver_variant(): 1 Riccati kernel alone, 2 Riccati screening + dense kernel
+    bool reset_failed = true;         // qmpc_config::reset_on_fail
     const double* x0_src = nullptr;   // where the next solve reads x0 / alpha from (own buffers or bound ones)
     const double* alpha_src = nullptr;
     int alpha_stride = 0;
@@ -90,6 +85,10 @@ struct qrgp_model {
     int B, M, device;
     double *X = nullptr, *theta = nullptr, *Kx = nullptr, *Kx_inv = nullptr;
     double *mu = nullptr, *C = nullptr, *alpha = nullptr, *xt = nullptr, *yt = nullptr;
+    double* part = nullptr;           // shared-swarm mode: per-CTA partial sums [3][part_ctas][M*M+M]
+    int sms = 148, part_ctas = 0, acc_warps = 0;
+    bool pushed = false;              // a regress has produced alpha since create / set_state: the reference pushes the RGP
+                                      // means into the solver only after its first regress (quad_opt.py:101,402-404)
 };
 
 struct qrgpl_model {
@@ -106,6 +105,8 @@ long long qmpc_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------- solver
 
+int qmpc_destroy(qmpc_handle_t h);
+
 int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
 {
     if (!cfg || !out) return fail(QMPC_ERR_ARG, "null argument");
@@ -114,13 +115,19 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     if (cfg->precision != 64 && cfg->precision != 32 && cfg->precision != 0) return fail(QMPC_ERR_ARG, "precision must be 64 or 32");
     if (cfg->n_basis > 0 && !cfg->gp_X) return fail(QMPC_ERR_ARG, "gp_X is NULL with n_basis > 0");
     if (!(cfg->t_horizon > 0) || !(cfg->ubu > cfg->lbu)) return fail(QMPC_ERR_ARG, "t_horizon / bounds invalid");
+    if (cfg->solver_variant < 0 || cfg->solver_variant > 2) return fail(QMPC_ERR_ARG, "solver_variant must be 0, 1 or 2");
+    if (cfg->solver_variant == 2 && (cfg->precision == 32 || cfg->n_nodes > DN_MAX_N))
+        return fail(QMPC_ERR_ARG, "solver_variant 2 (screening + dense) needs fp64 and n_nodes <= 21");
     CU_TRY(cudaSetDevice(cfg->device));
-    qmpc_solver* h = new qmpc_solver();
+    // every early return below releases what was allocated so far
+    std::unique_ptr<qmpc_solver, int (*)(qmpc_handle_t)> guard(new qmpc_solver(), qmpc_destroy);
+    qmpc_solver* h = guard.get();
     h->cfg = *cfg;
     if (h->cfg.precision == 0) h->cfg.precision = 64;
     h->cfg.gp_X = nullptr;
     h->dt = cfg_dt(*cfg);
     h->rsz = h->cfg.precision == 64 ? 8 : 4;
+    h->reset_failed = cfg->reset_on_fail >= 0;
     const size_t B = cfg->batch, N = cfg->n_nodes, M = cfg->n_basis;
     fill_model(*cfg, h->mp64);
 #define ALLOC(p, n) CU_TRY(cudaMalloc(reinterpret_cast<void**>(&(p)), (n)))
@@ -129,9 +136,8 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     ALLOC(h->u0, B * NU * 8); ALLOC(h->cost, B * 8); ALLOC(h->status, B * 4); ALLOC(h->iters, B * 4);
     ALLOC(h->xt, B * 3 * 8); ALLOC(h->yt, B * 3 * 8); ALLOC(h->rounds, B * 4); ALLOC(h->act, B * N * NU);
     ALLOC(h->fail_streak, B * 4);
-    ALLOC(h->W, B * N * WT * h->rsz); ALLOC(h->fac, B * N * FAC * h->rsz);
+    ALLOC(h->W, (B * N + 1) * WT * h->rsz); ALLOC(h->fac, B * N * FAC * h->rsz);
     ALLOC(h->gpX, 3 * (M ? M : 1) * 8);
-    ALLOC(h->xtr, B * (N + 1) * NX * h->rsz); ALLOC(h->ws, B * 5 * N * NU * h->rsz);
 #undef ALLOC
     CU_TRY(cudaMemset(h->x0, 0, B * NX * 8)); CU_TRY(cudaMemset(h->yref, 0, B * N * NY * 8));
     CU_TRY(cudaMemset(h->yref_e, 0, B * NX * 8)); CU_TRY(cudaMemset(h->alpha, 0, B * 3 * (M ? M : 1) * 8));
@@ -146,34 +152,22 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-    h->variant = getenv("QMPC_IPM_VARIANT") ? atoi(getenv("QMPC_IPM_VARIANT")) : (h->cfg.precision == 64 ? 2 : 0);
-    if (h->cfg.precision != 64 && h->variant >= 2) h->variant -= 2;     // the condensed formulation is fp64-only
-    const size_t smem2 = (size_t)2 * IPM2_WARPS * ipm2_smem_reals((int)N) * 8;
-    if ((h->variant == 1 || h->variant == 3) && smem2 > 220 * 1024) h->variant = 0;
-    if (h->variant == 1 || h->variant == 3) {
-        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<double, IPM2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<float, IPM2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2 / 2));
-        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<double, IPM2_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CU_TRY(cudaFuncSetAttribute(qmpc_ipm2_kernel<float, IPM2_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
-    if ((h->variant == 2 || h->variant == 3) && N > DN_MAX_N) h->variant -= 2;
-    if (h->variant == 2 || h->variant == 3) {
+    h->variant = solver_variant(h->cfg, DN_MAX_N);
+    if (h->variant == 2) {
         const int smemd = dense_layout((int)N).total * 8;
         CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->hard), (B + 1) * sizeof(int)));
         CU_TRY(cudaMemset(h->hard, 0, (B + 1) * sizeof(int)));
         CU_TRY(cudaFuncSetAttribute(qmpc_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
-        CU_TRY(cudaFuncSetAttribute(qmpc_dense_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd / 2));
         int per_sm = 0, sms = 0;
-        if (h->cfg.precision == 64) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<double>, DN_THREADS, smemd));
-        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<float>, DN_THREADS, smemd / 2));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<double>, DN_THREADS, smemd));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
         // persistent CTAs looping over the hard list: about 5 % of the vehicles are on it in steady state, so a sixth of
         // the batch (at most one resident wave) covers it without queueing empty CTAs behind other streams' kernels
-        const size_t want = getenv("QMPC_DENSE_GRID") ? (size_t)atol(getenv("QMPC_DENSE_GRID")) : std::max<size_t>(32, B / 6);
+        const size_t want = cfg->dense_grid > 0 ? (size_t)cfg->dense_grid : std::max<size_t>(32, B / 6);
         h->dense_grid = (int)std::min<size_t>(std::min<size_t>(B, want), (size_t)std::max(1, per_sm) * sms);
     }
     CU_TRY(cudaDeviceSynchronize());
-    *out = h;
+    *out = guard.release();
     return QMPC_OK;
 }
 
@@ -182,8 +176,10 @@ int qmpc_destroy(qmpc_handle_t h)
     if (!h) return QMPC_OK;
     cudaSetDevice(h->cfg.device);
     void* ps[] = {h->x0, h->yref, h->yref_e, h->alpha, h->xit, h->uit, h->u0, h->cost, h->status, h->iters,
-                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act, h->xtr, h->ws, h->timeline, h->hard, h->fail_streak};
+                  h->W, h->fac, h->gpX, h->xt, h->yt, h->rounds, h->act, h->timeline, h->hard, h->fail_streak};
     for (void* p : ps) if (p) cudaFree(p);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_mid) cudaEventDestroy(e);
     delete h;
     return QMPC_OK;
 }
@@ -275,8 +271,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
         h->ev.push_back(e0); h->ev.push_back(e1); h->ev.push_back(e2);
         CU_TRY(cudaEventRecord(e0, S(stream)));
     }
-    static const bool reset_failed = !(getenv("QMPC_RESET_ON_FAIL") && atoi(getenv("QMPC_RESET_ON_FAIL")) == 0);
-    if (reset_failed) {
+    if (h->reset_failed) {
         reset_failed_kernel<<<cdiv((long long)B * (N + 1), 256), 256, 0, S(stream)>>>(B, N, h->status, h->yref, h->yref_e, h->xit, h->uit, h->act, h->fail_streak);
         LAUNCH_CHECK();
     }
@@ -289,41 +284,19 @@ static int solve_impl(qmpc_solver* h, void* stream)
     ia.W = static_cast<const real*>(h->W); ia.fac = static_cast<real*>(h->fac);
     ia.u0 = h->u0; ia.cost = h->cost; ia.status = h->status; ia.iters = h->iters; ia.rounds = h->rounds; ia.act = h->act;
     ia.timeline = h->timeline;
-    if (reset_failed) ia.fail_streak = h->fail_streak;
-    static const int final_rollout = getenv("QMPC_FINAL_ROLLOUT") ? atoi(getenv("QMPC_FINAL_ROLLOUT")) : 0;
-    ia.final_rollout = final_rollout;
-    // QMPC_IPM_SMEM_PAD (bytes per CTA, tuning only): trades resident warps for L1 capacity
-    static const size_t pad = getenv("QMPC_IPM_SMEM_PAD") ? (size_t)atol(getenv("QMPC_IPM_SMEM_PAD")) : 0;
-    const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real) + pad;
-    if (h->variant == 1) {
-        Ipm2Args<real> i2;
-        i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N);
-        i2.xtr = static_cast<real*>(h->xtr); i2.ws = static_cast<real*>(h->ws);
-        const size_t smem2 = (size_t)2 * IPM2_WARPS * i2.b.smem_per_warp * sizeof(real) + pad;
-        qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
-    } else if (h->variant == 2 || h->variant == 3) {
-        // screening: warm-started active-set rounds in a Riccati kernel; whatever does not settle goes to the dense kernel
-        static const int screen_rounds = getenv("QMPC_SCREEN_ROUNDS") ? atoi(getenv("QMPC_SCREEN_ROUNDS")) : 3;
-        CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
-        ia.hard_list = h->hard; ia.hard_count = h->hard + B;
-        if (ia.warm_rounds > screen_rounds) ia.warm_rounds = screen_rounds;
-        static const int bail_round = getenv("QMPC_BAIL_ROUND") ? atoi(getenv("QMPC_BAIL_ROUND")) : 2;
-        static const int bail_changed = getenv("QMPC_BAIL_CHANGED") ? atoi(getenv("QMPC_BAIL_CHANGED")) : (1 << 20);
-        ia.bail_round = bail_round; ia.bail_changed = bail_changed;
-        static const int dense_warm = getenv("QMPC_DENSE_WARM_ROUNDS") ? atoi(getenv("QMPC_DENSE_WARM_ROUNDS")) : 8;
-        ia.dense_warm_rounds = dense_warm;
-        if (h->variant == 3) {
-            Ipm2Args<real> i2;
-            i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N);
-            i2.xtr = static_cast<real*>(h->xtr); i2.ws = static_cast<real*>(h->ws);
-            const size_t smem2 = (size_t)2 * IPM2_WARPS * i2.b.smem_per_warp * sizeof(real) + pad;
-            qmpc_ipm2_kernel<real, IPM2_WARPS><<<cdiv(B, 2 * IPM2_WARPS), IPM2_WARPS * 32, smem2, S(stream)>>>(i2);
-        } else {
-            ia.smem_per_warp = ipm_smem_reals_screen(N);
-            const size_t smem_s = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real) + pad;
+    if (h->reset_failed) ia.fail_streak = h->fail_streak;
+    if (h->variant == 2) {
+        // screening: warm-started active-set rounds in a Riccati kernel; whatever does not settle goes to the dense kernel.
+        // With the warm start off there is nothing to screen: the dense kernel takes every OCP from its cold IPM.
+        fill_screen_args(h->cfg, ia);
+        const bool screen = ia.warm_rounds > 0;
+        if (screen) {
+            CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
+            ia.hard_list = h->hard; ia.hard_count = h->hard + B;
+            const size_t smem_s = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real);
             qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem_s, S(stream)>>>(ia);
+            LAUNCH_CHECK();
         }
-        LAUNCH_CHECK();
         if (e2) {
             cudaEvent_t em = nullptr;
             CU_TRY(cudaEventCreate(&em));
@@ -331,10 +304,14 @@ static int solve_impl(qmpc_solver* h, void* stream)
             CU_TRY(cudaEventRecord(em, S(stream)));
         }
         DenseArgs<real> dn;
-        dn.b = ia; dn.hard_list = h->hard; dn.hard_count = h->hard + B;
-        qmpc_dense_kernel<real><<<h->dense_grid, DN_THREADS, dense_layout(N).total * sizeof(real), S(stream)>>>(dn);
-    } else
+        dn.b = ia;
+        dn.hard_list = screen ? h->hard : nullptr; dn.hard_count = screen ? h->hard + B : nullptr;
+        if constexpr (sizeof(real) == 8)
+            qmpc_dense_kernel<real><<<h->dense_grid, DN_THREADS, dense_layout(N).total * sizeof(real), S(stream)>>>(dn);
+    } else {
+        const size_t smem = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real);
         qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem, S(stream)>>>(ia);
+    }
     LAUNCH_CHECK();
     if (e2) CU_TRY(cudaEventRecord(e2, S(stream)));
     return QMPC_OK;
@@ -375,10 +352,24 @@ int qmpc_get_status(qmpc_handle_t h, int* status, int* iters, void* stream)
     if (iters) { int rc = copy_dd(iters, h->iters, (size_t)h->cfg.batch * 4, stream); if (rc) return rc; }
     return QMPC_OK;
 }
+int qmpc_get_fail_streak(qmpc_handle_t h, int* streak, void* stream)
+{
+    if (!h || !streak) return fail(QMPC_ERR_ARG, "null argument");
+    return copy_dd(streak, h->fail_streak, (size_t)h->cfg.batch * 4, stream);
+}
 int qmpc_get_refine_rounds(qmpc_handle_t h, int* rounds, void* stream)
 {
     if (!h) return fail(QMPC_ERR_ARG, "null handle");
     return copy_dd(rounds, h->rounds, (size_t)h->cfg.batch * 4, stream);
+}
+int qmpc_get_hard_count(qmpc_handle_t h, int* count_host, void* stream)
+{
+    if (!h || !count_host) return fail(QMPC_ERR_ARG, "null argument");
+    *count_host = 0;
+    if (!h->hard) return QMPC_OK;
+    CU_TRY(cudaMemcpyAsync(count_host, h->hard + h->cfg.batch, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    CU_TRY(cudaStreamSynchronize(S(stream)));
+    return QMPC_OK;
 }
 int qmpc_reset_warm_start(qmpc_handle_t h, void* stream)
 {
@@ -452,19 +443,40 @@ int qmpc_plant_period(const double* quad, const double* plant, int B, double* x,
 
 // ---------------------------------------------------------------------------------------------- RGP
 
+int qrgp_destroy(qrgp_handle_t g);
+
 int qrgp_create(int batch, int n_basis, const double* X, const double* theta, const double* Kx, const double* Kx_inv,
                 int device, qrgp_handle_t* out)
 {
     if (!X || !theta || !Kx || !Kx_inv || !out) return fail(QMPC_ERR_ARG, "null argument");
     if (batch < 1 || n_basis < 1 || n_basis > 32 * RGP_MAXT) return fail(QMPC_ERR_ARG, "batch/n_basis out of range");
     CU_TRY(cudaSetDevice(device));
-    qrgp_model* g = new qrgp_model();
+    std::unique_ptr<qrgp_model, int (*)(qrgp_handle_t)> guard(new qrgp_model(), qrgp_destroy);
+    qrgp_model* g = guard.get();
     g->B = batch; g->M = n_basis; g->device = device;
+    CU_TRY(cudaDeviceGetAttribute(&g->sms, cudaDevAttrMultiProcessorCount, device));
     const size_t B = batch, M = n_basis;
 #define ALLOC(p, n) CU_TRY(cudaMalloc(reinterpret_cast<void**>(&(p)), (n)))
     ALLOC(g->X, 3 * M * 8); ALLOC(g->theta, 9 * 8); ALLOC(g->Kx, 3 * M * M * 8); ALLOC(g->Kx_inv, 3 * M * M * 8);
     ALLOC(g->mu, B * 3 * M * 8); ALLOC(g->C, B * 3 * M * M * 8); ALLOC(g->alpha, B * 3 * M * 8);
     ALLOC(g->xt, B * 3 * 8); ALLOC(g->yt, B * 3 * 8);
+    if (batch == 1) {
+        // shared-swarm mode: per-CTA partial sums of the information-form accumulate (no atomics: fixed summation order)
+        const size_t per_warp = (size_t)(M * M + 3 * M) * 8;
+        int warps = int((200 * 1024) / per_warp);
+        g->acc_warps = warps > 8 ? 8 : warps;
+        g->part_ctas = g->sms;
+        if (g->acc_warps >= 1) {
+            ALLOC(g->part, (size_t)3 * g->part_ctas * (M * M + M) * 8);
+            const int smem = (int)(per_warp * g->acc_warps);
+#define SHARED_ATTR(W) case W: CU_TRY(cudaFuncSetAttribute(qrgp_shared_accumulate_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); break;
+            switch (g->acc_warps) { SHARED_ATTR(1) SHARED_ATTR(2) SHARED_ATTR(3) SHARED_ATTR(4) SHARED_ATTR(5) SHARED_ATTR(6) SHARED_ATTR(7) SHARED_ATTR(8) }
+#undef SHARED_ATTR
+        }
+        const size_t smem_apply = (size_t)M * (2 * M + 1) * 8;
+        if (smem_apply <= 220 * 1024)
+            CU_TRY(cudaFuncSetAttribute(qrgp_shared_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply));
+    }
 #undef ALLOC
     CU_TRY(cudaMemcpy(g->X, X, 3 * M * 8, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(g->theta, theta, 9 * 8, cudaMemcpyHostToDevice));
@@ -472,10 +484,10 @@ int qrgp_create(int batch, int n_basis, const double* X, const double* theta, co
     CU_TRY(cudaMemcpy(g->Kx_inv, Kx_inv, 3 * M * M * 8, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(g->mu, 0, B * 3 * M * 8));
     CU_TRY(cudaMemset(g->alpha, 0, B * 3 * M * 8));
-    for (size_t b = 0; b < B; ++b)   // C0 = K_x for every vehicle (RGP.py:144)
-        CU_TRY(cudaMemcpyAsync(g->C + b * 3 * M * M, g->Kx, 3 * M * M * 8, cudaMemcpyDeviceToDevice, 0));
+    qrgp_fill_C_kernel<<<cdiv((long long)B * 3 * M * M, 256), 256>>>((long long)B, 3 * (int)M * (int)M, g->Kx, g->C);   // C0 = K_x for every vehicle (RGP.py:144)
+    LAUNCH_CHECK();
     CU_TRY(cudaDeviceSynchronize());
-    *out = g;
+    *out = guard.release();
     return QMPC_OK;
 }
 
@@ -483,7 +495,7 @@ int qrgp_destroy(qrgp_handle_t g)
 {
     if (!g) return QMPC_OK;
     cudaSetDevice(g->device);
-    void* ps[] = {g->X, g->theta, g->Kx, g->Kx_inv, g->mu, g->C, g->alpha, g->xt, g->yt};
+    void* ps[] = {g->X, g->theta, g->Kx, g->Kx_inv, g->mu, g->C, g->alpha, g->xt, g->yt, g->part};
     for (void* p : ps) if (p) cudaFree(p);
     delete g;
     return QMPC_OK;
@@ -497,6 +509,7 @@ static int regress_launch(qrgp_model* g, const double* xt, const double* yt, voi
     const size_t smem = (size_t)RGP_WARPS * 3 * g->M * 8;
     qrgp_regress_kernel<RGP_WARPS><<<cdiv((long long)g->B * 3, RGP_WARPS), RGP_WARPS * 32, smem, S(stream)>>>(a);
     LAUNCH_CHECK();
+    g->pushed = true;
     return QMPC_OK;
 }
 
@@ -541,6 +554,7 @@ int qrgp_set_state(qrgp_handle_t g, const double* mu, const double* C, void* str
         qrgp_alpha_kernel<<<cdiv((long long)g->B * 3 * g->M, 128), 128, 0, S(stream)>>>(g->B, g->M, g->Kx_inv, g->mu, g->alpha);
         LAUNCH_CHECK();
     }
+    g->pushed = false;      // like the reference, a loaded/assigned model reaches the solver with the next regress
     if (C) return copy_dd(g->C, C, (size_t)g->B * 3 * g->M * g->M * 8, stream);
     return QMPC_OK;
 }
@@ -585,28 +599,24 @@ int qrgp_predict_using_y(qrgp_handle_t g, int m, const double* xs, const double*
 int qrgp_shared_accumulate(qrgp_handle_t g, int B, const double* xt, const double* yt, double* info, void* stream)
 {
     if (!g || !xt || !yt || !info || B < 1) return fail(QMPC_ERR_ARG, "bad argument");
-    const int M = g->M;
+    if (g->B != 1 || !g->part) return fail(QMPC_ERR_ARG, "shared model handles must be created with batch == 1 (n_basis small enough for the accumulate tile)");
+    const int M = g->M, warps = g->acc_warps;
     const size_t per_warp = (size_t)(M * M + 3 * M) * 8;
-    int warps = int((200 * 1024) / per_warp);
-    warps = warps > 8 ? 8 : warps;
-    if (warps < 1) return fail(QMPC_ERR_ARG, "n_basis too large for the shared accumulate tile");
     RgpSharedArgs a;
-    a.B = B; a.M = M; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.xt = xt; a.yt = yt; a.info = info;
-    CU_TRY(cudaMemsetAsync(info, 0, (size_t)3 * (M * M + M) * 8, S(stream)));
+    a.B = B; a.M = M; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.xt = xt; a.yt = yt; a.part = g->part;
     int blocks = cdiv(B, warps * 8);
-    blocks = blocks > 148 ? 148 : blocks;
+    blocks = blocks > g->part_ctas ? g->part_ctas : blocks;
     dim3 grid(blocks, 3);
     const size_t smem = per_warp * warps;
-#define SHARED_LAUNCH(W)                                                                                         \
-    case W:                                                                                                      \
-        CU_TRY(cudaFuncSetAttribute(qrgp_shared_accumulate_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        qrgp_shared_accumulate_kernel<W><<<grid, W * 32, smem, S(stream)>>>(a);                                  \
-        break;
+#define SHARED_LAUNCH(W) case W: qrgp_shared_accumulate_kernel<W><<<grid, W * 32, smem, S(stream)>>>(a); break;
     switch (warps) {
         SHARED_LAUNCH(1) SHARED_LAUNCH(2) SHARED_LAUNCH(3) SHARED_LAUNCH(4)
         SHARED_LAUNCH(5) SHARED_LAUNCH(6) SHARED_LAUNCH(7) SHARED_LAUNCH(8)
     }
 #undef SHARED_LAUNCH
+    LAUNCH_CHECK();
+    // second stage: fixed-order sum of the per-CTA partials (results are bit-reproducible run to run)
+    qrgp_shared_reduce_kernel<<<dim3(cdiv(M * M + M, 256), 3), 256, 0, S(stream)>>>(M * M + M, blocks, g->part_ctas, g->part, info);
     LAUNCH_CHECK();
     return QMPC_OK;
 }
@@ -618,9 +628,9 @@ int qrgp_shared_apply(qrgp_handle_t g, const double* info, void* stream)
     const int M = g->M;
     const size_t smem = (size_t)M * (2 * M + 1) * 8;
     if (smem > 220 * 1024) return fail(QMPC_ERR_ARG, "n_basis too large for the shared apply tile");
-    CU_TRY(cudaFuncSetAttribute(qrgp_shared_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     qrgp_shared_apply_kernel<<<3, 256, smem, S(stream)>>>(M, info, g->mu, g->C, g->Kx_inv, g->alpha);
     LAUNCH_CHECK();
+    g->pushed = true;
     return QMPC_OK;
 }
 
@@ -636,7 +646,9 @@ int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const doubl
     set_reference_kernel<<<cdiv((long long)B * N * NY, 256), 256, 0, S(stream)>>>(B, N, x_ref, nullptr, 0.16, h->yref, h->yref_e);
     LAUNCH_CHECK();
     h->x0_src = x_now;
-    if (g) { h->alpha_src = g->alpha; h->alpha_stride = g->B == 1 ? 0 : 3 * g->M; }
+    // the reference's solver parameters are whatever was last pushed: zeros (or qmpc_set_params/alpha) until the first
+    // regress of this model (quad_opt.py:101,402-404)
+    if (g && g->pushed) { h->alpha_src = g->alpha; h->alpha_stride = g->B == 1 ? 0 : 3 * g->M; }
     int rc = qmpc_solve(h, stream);
     h->x0_src = h->x0;
     if (g) { h->alpha_src = h->alpha; h->alpha_stride = 3 * h->cfg.n_basis; }

@@ -30,8 +30,6 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
 inline int ipm_smem_reals(int N) { return (SM_VEC + SM_NVEC * 4 * N + (N + 1) * 13 + 9) & ~1; }
 inline int ipm_smem_reals_screen(int N) { return (SM_VEC + 7 * 4 * N + (N + 1) * 13 + 9) & ~1; }   // screening mode layout
-// two-OCPs-per-warp kernel: per-OCP reals, = 8 mod 16 so that the two OCPs of a warp sit half a bank row apart
-inline int ipm2_smem_reals(int N) { int n = 360 + 8 * 4 * N; n += (24 - (n % 16)) % 16; return n; }
 
 template <typename real>
 inline void fill_lin_args(const qmpc_config& c, LinArgs<real>& a)
@@ -63,8 +61,32 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.post_bail = f64 ? 0 : 1;
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes);
-    a.bail_round = 2; a.bail_changed = 1 << 20; a.final_rollout = 0; a.dense_warm_rounds = 0;
+    a.bail_round = c.bail_round > 0 ? c.bail_round : 2;
+    a.bail_changed = c.bail_changed > 0 ? c.bail_changed : (1 << 20);
+    a.final_rollout = c.final_rollout > 0 ? 1 : 0;
+    a.dense_warm_rounds = 0;
     a.timeline = nullptr; a.hard_list = nullptr; a.hard_count = nullptr;
+}
+
+// 1 = Riccati kernel alone, 2 = Riccati screening launch + dense condensed launch (qmpc_config::solver_variant, 0 = auto)
+inline int solver_variant(const qmpc_config& c, int dense_max_nodes)
+{
+    const bool dense_ok = c.precision != 32 && c.n_nodes <= dense_max_nodes;     // the condensed formulation is fp64-only
+    if (c.solver_variant == 1 || !dense_ok) return 1;
+    return 2;
+}
+
+// screening-mode arguments (variant 2): the screening launch tries `screen_rounds` warm-started rounds, the dense launch
+// continues for `dense_warm_rounds`; with the warm start switched off (warm_start_rounds < 0) neither kernel looks at
+// the remembered active set and every OCP takes the cold IPM of the dense kernel.
+template <typename real>
+inline void fill_screen_args(const qmpc_config& c, IpmArgs<real>& a)
+{
+    const int screen = c.screen_rounds > 0 ? c.screen_rounds : 3;
+    const int dense_warm = c.dense_warm_rounds < 0 ? 0 : (c.dense_warm_rounds == 0 ? 8 : c.dense_warm_rounds);
+    a.dense_warm_rounds = a.warm_rounds > 0 ? dense_warm : 0;
+    if (a.warm_rounds > screen) a.warm_rounds = screen;
+    a.smem_per_warp = ipm_smem_reals_screen(c.n_nodes);
 }
 
 }  // namespace qmpc

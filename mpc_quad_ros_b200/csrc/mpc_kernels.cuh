@@ -155,6 +155,17 @@ struct IpmArgs {
     int* hard_count;               // appended here for the dense kernel instead of running the IPM in this warp
 };
 
+// IPM iteration limit of this solve: a vehicle whose last two or more solves failed gets a bounded attempt, except every
+// eighth failure in a row, which gets the full limit again (a reset problem that needs more than max_iter_failed
+// iterations must not stay failed for ever)
+template <typename real>
+__device__ __forceinline__ int iter_limit(const IpmArgs<real>& a, int ocp)
+{
+    if (!a.fail_streak) return a.max_iter;
+    const int s = a.fail_streak[ocp];
+    return (s >= 2 && (s & 7) != 0) ? a.max_iter_failed : a.max_iter;
+}
+
 __device__ __forceinline__ long long global_ns()
 {
 #ifdef QMPC_EMU
@@ -790,7 +801,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
                     if (!refine && mu < target) { status = QMPC_STATUS_OK_; break; }
                 } else { status = QMPC_STATUS_OK_; break; }
             }
-            if (it >= ((a.fail_streak && a.fail_streak[ocp] >= 2) ? a.max_iter_failed : a.max_iter)) break;
+            if (it >= iter_limit(a, ocp)) break;
             // predictor
             for (int e = lane; e < E; e += 32) {
                 const real d = c.ll[e] / c.tl[e] + c.lu[e] / c.tu[e];

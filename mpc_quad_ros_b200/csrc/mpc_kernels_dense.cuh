@@ -10,7 +10,7 @@
 // per right-hand side stay serial (one warp, shuffles).  Same algorithm as the Riccati path: Mehrotra IPM from the
 // box centre with gradient-scaled multipliers, hand-over to exact primal-dual active-set rounds, full step.
 #pragma once
-#include "mpc_kernels_v2.cuh"
+#include "mpc_kernels.cuh"
 
 namespace qmpc {
 
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                             }
                             next = T_FIXED; rounds_left = a.max_refine; prev_changed = 1 << 30; round_no = 0;
                         } else { status = QMPC_STATUS_OK_; next = T_DONE; }
-                    } else if (it >= ((a.fail_streak && a.fail_streak[ocp] >= 2) ? a.max_iter_failed : a.max_iter)) next = T_DONE;
+                    } else if (it >= iter_limit(a, ocp)) next = T_DONE;
                 }
                 __syncwarp();
                 if (lane == 0) ctl[0] = next;

@@ -237,11 +237,12 @@ struct RgpSharedArgs {
     const double* X; const double* theta; const double* Kx_inv;
     const double* xt;   // [B][3]
     const double* yt;   // [B][3]
-    double* info;       // [3][M*M + M]  (Lambda row-major, then eta), accumulated with atomics
+    double* part;       // [3][gridDim.x][M*M + M]  per-CTA partial sums (Lambda row-major, then eta)
 };
 
 // Each warp walks a strided subset of vehicles for one axis and accumulates j^T j / r and j^T y / r into a
-// warp-private shared-memory tile; one atomicAdd per entry per warp at the end.
+// warp-private shared-memory tile; the CTA adds its warps' tiles in warp order and writes ONE partial block, which
+// qrgp_shared_reduce_kernel sums over CTAs in CTA order: no atomics anywhere, so the result is bit-reproducible.
 // dynamic smem per warp: (M*M + 3*M) doubles
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) qrgp_shared_accumulate_kernel(RgpSharedArgs a)
@@ -276,9 +277,33 @@ __global__ void __launch_bounds__(WARPS * 32) qrgp_shared_accumulate_kernel(RgpS
         for (int t = lane; t < M * M; t += 32) { const int i = t / M, j = t - i * M; acc[t] += Jt[i] * Jt[j] * rinv; }
         for (int i = lane; i < M; i += 32) eta[i] += Jt[i] * yt * rinv;
     }
-    __syncwarp();
-    double* out = a.info + (size_t)d * (M * M + M);
-    for (int t = lane; t < M * M + M; t += 32) atomicAdd(out + t, acc[t]);
+    __syncthreads();
+    double* out = a.part + ((size_t)d * gridDim.x + blockIdx.x) * (M * M + M);
+    const double* base = reinterpret_cast<double*>(smem_raw);
+    for (int t = threadIdx.x; t < M * M + M; t += WARPS * 32) {
+        double s = 0;
+        for (int w = 0; w < WARPS; ++w) s += base[(size_t)w * (M * M + 3 * M) + t];
+        out[t] = s;
+    }
+}
+
+// info[d][t] = sum over the `ctas` partial blocks of axis d, in CTA order
+__global__ void qrgp_shared_reduce_kernel(int len, int ctas, int stride_ctas, const double* __restrict__ part, double* __restrict__ info)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y;
+    if (t >= len) return;
+    const double* p = part + (size_t)d * ctas * len + t;
+    double s = 0;
+    for (int c = 0; c < ctas; ++c) s += p[(size_t)c * len];
+    info[(size_t)d * len + t] = s;
+    (void)stride_ctas;
+}
+
+// C0 = K_x for every vehicle and axis (RGP.py:144): C[b][e] = Kx[e]
+__global__ void qrgp_fill_C_kernel(long long B, int per, const double* __restrict__ Kx, double* __restrict__ C)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B * per) C[t] = Kx[t % per];
 }
 
 // Posterior of the shared model after the all-reduce (one CTA per axis, Gauss-Jordan in shared memory):

@@ -21,7 +21,12 @@ R_COST = np.array([0.1, 0.1, 0.1, 0.1])
 
 class quad_optimizer:
     def __init__(self, quad, t_horizon=1, n_nodes=100, gpe=None, batch=None, device=None, precision=64,
-                 ipm_mu_tol=0.0, ipm_max_iter=50, ipm_mu_switch=0.0, refine_max_rounds=0, warm_start_rounds=0):
+                 ipm_mu_tol=0.0, ipm_max_iter=50, ipm_mu_switch=0.0, refine_max_rounds=0, warm_start_rounds=0,
+                 solver_variant=0, reset_on_fail=0, screen_rounds=0, dense_warm_rounds=0, bail_round=0, bail_changed=0,
+                 final_rollout=0, dense_grid=0):
+        """The arguments after `gpe` have no counterpart in the reference (one vehicle, acados defaults): batch/device/
+        precision select the GPU path, the rest is the per-handle solver policy of include/qmpc.h (0 = library default;
+        reset_on_fail=-1 keeps whatever a failed solve left, which is what the reference does, quad_opt.py:333)."""
         self.n_nodes, self.t_horizon, self.gpe = n_nodes, t_horizon, gpe
         self.optimization_dt = self.t_horizon / self.n_nodes
         self.terminal_cost = 1
@@ -43,7 +48,10 @@ class quad_optimizer:
         cfg.precision, cfg.device = precision, (self.device.index or 0)
         cfg.ipm_max_iter, cfg.ipm_mu_tol, cfg.t_horizon = ipm_max_iter, ipm_mu_tol, float(t_horizon)
         cfg.ipm_mu_switch, cfg.refine_max_rounds = ipm_mu_switch, refine_max_rounds   # 0 -> library defaults
-        cfg.warm_start_rounds = warm_start_rounds                                     # 0 -> 3 rounds, <0 -> cold IPM every step
+        cfg.warm_start_rounds = warm_start_rounds                                     # 0 -> 6 rounds, <0 -> cold IPM every step
+        cfg.solver_variant, cfg.reset_on_fail, cfg.screen_rounds = solver_variant, reset_on_fail, screen_rounds
+        cfg.dense_warm_rounds, cfg.bail_round, cfg.bail_changed = dense_warm_rounds, bail_round, bail_changed
+        cfg.final_rollout, cfg.dense_grid = final_rollout, dense_grid
         cfg.quad[:] = list(quad.quad_vector())
         cfg.w_diag[:] = list(np.diag(self.W))
         cfg.we_diag[:] = list(np.diag(self.W_e))
@@ -140,6 +148,12 @@ class quad_optimizer:
         it = torch.empty_like(st)
         _capi.check(_capi.lib().qmpc_get_status(self._h, _capi.ptr(st), _capi.ptr(it), self._s()))
         return st, it
+
+    def fail_streak(self):
+        """consecutive failed solves per vehicle (0 = the last solve was fine), [B] int32"""
+        r = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+        _capi.check(_capi.lib().qmpc_get_fail_streak(self._h, _capi.ptr(r), self._s()))
+        return r
 
     def solver_rounds(self):
         """active-set refinement rounds of the last solve (warm-start rounds + rounds after the IPM), [B] int32"""

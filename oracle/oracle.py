@@ -213,7 +213,7 @@ class ClosedLoop:
     """B independent vehicles, persistent controller state, order of execute_trajectory.py:196-277."""
 
     def __init__(self, quad, dt, N, traj, x_init, gp=None, plant=PLANT_DEFAULT, sim_dt=5e-3, u_ref=0.16,
-                 mu_tol=1e-13, max_iter=60, polish=True, nthreads=0):
+                 mu_tol=1e-13, max_iter=60, polish=True, nthreads=0, reset_on_fail=False):
         self.quad, self.dt, self.N, self.gp = _c(quad), float(dt), int(N), gp
         self.traj = _c(traj)
         self.B, self.K = self.traj.shape[0], self.traj.shape[1]
@@ -231,6 +231,7 @@ class ClosedLoop:
         self.have_pred = np.zeros(self.B, dtype=np.int32)
         self.plant, self.sim_dt, self.u_ref = _c(plant), float(sim_dt), float(u_ref)
         self.mu_tol, self.max_iter, self.polish, self.nthreads = mu_tol, max_iter, polish, nthreads
+        self.reset_on_fail = bool(reset_on_fail)     # False = reference semantics (solver status ignored, quad_opt.py:333)
         self.step_idx = 0
 
     def run(self, steps, log=True):
@@ -245,7 +246,7 @@ class ClosedLoop:
             _p(gp.X if gp else None), _p(gp.theta if gp else None), _p(gp.Kx_inv if gp else None), int(gp is not None),
             _p(_c(W_DIAG)), _p(_c(WE_DIAG)), _d(self.u_ref), B, self.K, _p(self.traj), self.step_idx, int(steps),
             _p(self.x), _p(self.xit), _p(self.uit), _p(self.mu), _p(self.C), _p(self.xpred_prev), _pi(self.have_pred),
-            _p(u0), _p(xl), _p(cl), _pi(il), _d(self.mu_tol), int(self.max_iter), int(self.polish), int(self.nthreads))
+            _p(u0), _p(xl), _p(cl), _pi(il), _d(self.mu_tol), int(self.max_iter), int(self.polish), int(self.nthreads), int(self.reset_on_fail))
         self.step_idx += steps
         return dict(bad=bad, u0=u0, x=xl, cost=cl, iters=il)
 

@@ -915,8 +915,10 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
                     double *x, double *xit, double *uit, double *mu, double *C,
                     double *xpred_prev, int *have_pred,
                     double *u0_log, double *x_log, double *cost_log, int *iters_log,
-                    double mu_tol, int max_iter, int do_polish, int nthreads)
+                    double mu_tol, int max_iter, int do_polish, int nthreads, int reset_on_fail)
 {
+    /* reset_on_fail = 0: the reference's behaviour, the iterate is whatever the last solve left (quad_opt.py:333 ignores
+     * the solver status).  reset_on_fail = 1 mirrors the library's per-handle option (include/qmpc.h reset_on_fail). */
     int bad = 0;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -938,7 +940,7 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
             }
             const double *yref_e = chunk + (N - 1) * NX;
             if (use_gp) for (int d = 0; d < 3; ++d) orc_rgp_alpha(M, Kx_inv + d * M * M, mub + d * M, alpha + d * M);
-            if (have_pred[b] >= 2) {      /* previous solve failed: restart the SQP iterate on the new reference */
+            if (reset_on_fail && have_pred[b] >= 2) {      /* previous solve failed: restart the SQP iterate on the new reference */
                 for (int k = 0; k < N; ++k) {
                     memcpy(xi + k * NX, chunk + k * NX, sizeof(double) * NX);
                     for (int a = 0; a < NU; ++a) ui[k * NU + a] = u_ref;
@@ -949,7 +951,7 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
             memcpy(xnow, xb, sizeof(xnow));
             int st = orc_rti_step(quad, dt, N, use_gp ? M : 0, gpX, gpth, use_gp ? alpha : NULL, Wd, Wed, 0.0, 1.0,
                                   xnow, yref, yref_e, xi, ui, &cost, &iters, &kkt, mu_tol,
-                                  (have_pred[b] >= 3 && max_iter > 20) ? 20 : max_iter,   /* two failures in a row: bounded attempt */
+                                  (reset_on_fail && have_pred[b] >= 3 && ((have_pred[b] - 1) & 7) != 0 && max_iter > 20) ? 20 : max_iter,   /* two failures in a row: bounded attempt, full again every 8th */
                                   do_polish, NULL);
             if (st > 1) bad += 1;
             double u0[NU], xpred[NX];

@@ -26,13 +26,17 @@ def lib():
 
 
 def make_config(B, N, t_horizon, quad, w_diag, we_diag, gp_X=None, gp_theta=None, mu_tol=0.0, max_iter=0,
-                lbu=0.0, ubu=1.0):
+                lbu=0.0, ubu=1.0, **policy):
+    """policy: any of the qmpc_config solver-policy fields (solver_variant, screen_rounds, warm_start_rounds, ...)"""
     c = QmpcConfig()
     c.batch, c.n_nodes, c.precision, c.device = B, N, 64, 0
     c.n_basis = 0 if gp_X is None else gp_X.shape[1]
     c.ipm_max_iter, c.ipm_mu_tol, c.t_horizon = max_iter, mu_tol, t_horizon
     c.quad[:] = list(quad); c.w_diag[:] = list(w_diag); c.we_diag[:] = list(we_diag)
     c.lbu, c.ubu = lbu, ubu
+    for k, v in policy.items():
+        assert hasattr(c, k), k
+        setattr(c, k, v)
     keep = None
     if gp_X is not None:
         keep = np.ascontiguousarray(gp_X, dtype=np.float64)
@@ -41,7 +45,8 @@ def make_config(B, N, t_horizon, quad, w_diag, we_diag, gp_X=None, gp_theta=None
     return c, keep
 
 
-def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None, variant=0):
+def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None, variant=None):
+    """variant: None = cfg.solver_variant as given; 1 = Riccati kernel alone, 2 = screening + dense kernel"""
     B, N = cfg.batch, cfg.n_nodes
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     x0, yref, yref_e = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, yref, yref_e))
@@ -50,6 +55,13 @@ def solve(cfg, x0, yref, yref_e, alpha, xit, uit, f32=False, act=None, variant=0
     status, iters, rounds = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     act = np.full((B, 4 * N), 255, dtype=np.uint8) if act is None else act
     W = np.empty((B, N, 13, 16), dtype=np.float32 if f32 else np.float64)
-    fn = getattr(lib(), "emu_solve%s_%s" % (("", "2", "3", "4")[variant], "f32" if f32 else "f64"))
-    fn(C.byref(cfg), p(x0), p(yref), p(yref_e), p(alpha), p(xit), p(uit), p(u0), p(cost), p(status), p(iters), p(rounds), p(act), p(W))
-    return dict(u0=u0, cost=cost, status=status, iters=iters, rounds=rounds, act=act, W=W)
+    saved_variant, saved_prec = cfg.solver_variant, cfg.precision
+    if variant is not None:
+        cfg.solver_variant = variant
+    cfg.precision = 32 if f32 else 64
+    hard = C.c_int(0)
+    fn = getattr(lib(), "emu_solve_%s" % ("f32" if f32 else "f64"))
+    fn(C.byref(cfg), p(x0), p(yref), p(yref_e), p(alpha), p(xit), p(uit), p(u0), p(cost), p(status), p(iters), p(rounds), p(act), p(W),
+       C.byref(hard))
+    cfg.solver_variant, cfg.precision = saved_variant, saved_prec
+    return dict(u0=u0, cost=cost, status=status, iters=iters, rounds=rounds, act=act, W=W, hard=hard.value)

@@ -3,7 +3,6 @@
 #define QMPC_EMU 1
 #include "emu_cuda.h"
 #include "../../mpc_quad_ros_b200/csrc/mpc_kernels.cuh"
-#include "../../mpc_quad_ros_b200/csrc/mpc_kernels_v2.cuh"
 #include "../../mpc_quad_ros_b200/csrc/mpc_kernels_dense.cuh"
 #include "../../mpc_quad_ros_b200/csrc/host_params.h"
 
@@ -12,10 +11,10 @@ using namespace qmpc;
 template <typename real>
 static int run_solve(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                      const double* alpha, double* xit, double* uit, double* u0, double* cost, int* status,
-                     int* iters, int* rounds, unsigned char* act, real* Wout, int variant = 0)
+                     int* iters, int* rounds, unsigned char* act, real* Wout, int* hard_out = nullptr)
 {
     const int B = o->batch, N = o->n_nodes;
-    std::vector<real> W((size_t)B * N * WT), fac((size_t)B * N * FAC);
+    std::vector<real> W(((size_t)B * N + 1) * WT), fac((size_t)B * N * FAC);
     LinArgs<real> la;
     fill_lin_args(*o, la);
     la.xit = xit; la.uit = uit; la.yref = yref; la.alpha = alpha; la.gpX = o->gp_X; la.W = W.data();
@@ -26,87 +25,39 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
     ia.x0 = x0; ia.yref = yref; ia.yref_e = yref_e; ia.xit = xit; ia.uit = uit; ia.W = W.data(); ia.fac = fac.data();
     ia.u0 = u0; ia.cost = cost; ia.status = status; ia.iters = iters; ia.rounds = rounds; ia.act = act;
     constexpr int WARPS = 4;
-    if (variant == 0) {
+    const int variant = solver_variant(*o, DN_MAX_N);      // the same dispatch as capi.cu solve_impl
+    if (hard_out) *hard_out = 0;
+    if (variant == 1) {
         emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
                     [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
-    } else if (variant == 2 || variant == 3) {      // screening kernel (warm-started rounds) + dense kernel for the rest
+    } else {      // screening kernel (warm-started rounds) + dense kernel for the rest
         std::vector<int> list(B), cnt(1, 0);
-        ia.hard_list = list.data(); ia.hard_count = cnt.data();
-        if (getenv("QMPC_SCREEN_ROUNDS") && ia.warm_rounds > atoi(getenv("QMPC_SCREEN_ROUNDS"))) ia.warm_rounds = atoi(getenv("QMPC_SCREEN_ROUNDS"));
-        if (getenv("QMPC_DENSE_WARM_ROUNDS")) ia.dense_warm_rounds = atoi(getenv("QMPC_DENSE_WARM_ROUNDS"));
-        if (variant == 2) {
+        fill_screen_args(*o, ia);
+        const bool screen = ia.warm_rounds > 0;
+        if (screen) {
+            ia.hard_list = list.data(); ia.hard_count = cnt.data();
             emu::launch((B + WARPS - 1) / WARPS, WARPS * 32, (size_t)WARPS * ia.smem_per_warp * sizeof(real),
                         [&]() { qmpc_ipm_kernel<real, WARPS>(ia); });
-        } else {
-            constexpr int W2 = 2;
-            std::vector<real> xtr((size_t)B * (N + 1) * NX), ws((size_t)B * 5 * 4 * N);
-            Ipm2Args<real> i2;
-            i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N); i2.xtr = xtr.data(); i2.ws = ws.data();
-            emu::launch((B + 2 * W2 - 1) / (2 * W2), W2 * 32, (size_t)2 * W2 * i2.b.smem_per_warp * sizeof(real),
-                        [&]() { qmpc_ipm2_kernel<real, W2>(i2); });
-        }
+            if (hard_out) *hard_out = cnt[0];
+        } else if (hard_out) *hard_out = B;
         DenseArgs<real> dn;
-        dn.b = ia; dn.hard_list = list.data(); dn.hard_count = cnt.data();
-        emu::launch(2, DN_THREADS, (size_t)dense_layout(N).total * sizeof(real), [&]() { qmpc_dense_kernel<real>(dn); });
-    } else {
-        constexpr int W2 = 2;
-        std::vector<real> xtr((size_t)B * (N + 1) * NX), ws((size_t)B * 5 * 4 * N);
-        Ipm2Args<real> i2;
-        i2.b = ia; i2.b.smem_per_warp = ipm2_smem_reals(N); i2.xtr = xtr.data(); i2.ws = ws.data();
-        emu::launch((B + 2 * W2 - 1) / (2 * W2), W2 * 32, (size_t)2 * W2 * i2.b.smem_per_warp * sizeof(real),
-                    [&]() { qmpc_ipm2_kernel<real, W2>(i2); });
+        dn.b = ia; dn.hard_list = screen ? list.data() : nullptr; dn.hard_count = screen ? cnt.data() : nullptr;
+        if constexpr (sizeof(real) == 8)
+            emu::launch(2, DN_THREADS, (size_t)dense_layout(N).total * sizeof(real), [&]() { qmpc_dense_kernel<real>(dn); });
     }
-    if (Wout) std::memcpy(Wout, W.data(), W.size() * sizeof(real));
+    if (Wout) std::memcpy(Wout, W.data(), (size_t)B * N * WT * sizeof(real));
     return 0;
 }
 
 extern "C" int emu_solve_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                             int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
+                             int* status, int* iters, int* rounds, unsigned char* act, double* Wout, int* hard_out)
 {
-    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout);
+    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, hard_out);
 }
 extern "C" int emu_solve_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                             int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
+                             int* status, int* iters, int* rounds, unsigned char* act, float* Wout, int* hard_out)
 {
-    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout);
-}
-
-extern "C" int emu_solve2_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
-                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                              int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
-{
-    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 1);
-}
-extern "C" int emu_solve3_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
-                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                              int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
-{
-    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 2);
-}
-extern "C" int emu_solve3_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
-                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
-{
-    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 2);
-}
-extern "C" int emu_solve2_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
-                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
-{
-    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 1);
-}
-
-extern "C" int emu_solve4_f64(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
-                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                              int* status, int* iters, int* rounds, unsigned char* act, double* Wout)
-{
-    return run_solve<double>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 3);
-}
-extern "C" int emu_solve4_f32(const HostOcp* o, const double* x0, const double* yref, const double* yref_e,
-                              const double* alpha, double* xit, double* uit, double* u0, double* cost,
-                              int* status, int* iters, int* rounds, unsigned char* act, float* Wout)
-{
-    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, 3);
+    return run_solve<float>(o, x0, yref, yref_e, alpha, xit, uit, u0, cost, status, iters, rounds, act, Wout, hard_out);
 }

@@ -25,14 +25,14 @@ def _pkg():
     return Quadrotor3D, quad_optimizer, GPEnsemble
 
 
-def _solve_batch(sc, B, N, gp, precision=64, quad_name="hummingbird", mu_tol=0.0):
+def _solve_batch(sc, B, N, gp, precision=64, quad_name="hummingbird", mu_tol=0.0, **policy):
     Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
     quad = Quadrotor3D(drag=True, batch=B)
     quad = quad.set_hummingbird_params() if quad_name == "hummingbird" else quad.set_logged_pysim_params()
     gpe = None
     if gp is not None:
         gpe = GPEnsemble.fromrange([(gp.X[d, 0], gp.X[d, -1]) for d in range(3)], [gp.M] * 3, theta=list(gp.theta[0]), batch=B)
-    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=precision, ipm_mu_tol=mu_tol)
+    opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=precision, ipm_mu_tol=mu_tol, **policy)
     opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
     dev = opt.device
     import ctypes as C
@@ -399,18 +399,16 @@ def test_grouped_streams_equal_single_stream():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
-def test_solver_kernel_variants_agree_with_oracle(variant, monkeypatch):
-    """QMPC_IPM_VARIANT selects the kernel mapping behind qmpc_solve (0 Riccati kernel alone, 1 two OCPs per warp,
-    2 = default: Riccati screening + dense condensed kernel, 3 two-OCP screening + dense).  Cold solve, then a warm-started
-    second solve from the returned iterate/active set: every mapping lands on the oracle's minimiser."""
-    monkeypatch.setenv("QMPC_IPM_VARIANT", str(variant))
-    B, N, M = 67, 20, 20                      # odd batch: idle half-warp / partial CTA paths
+@pytest.mark.parametrize("variant", [1, 2])
+def test_solver_kernel_variants_agree_with_oracle(variant):
+    """qmpc_config.solver_variant selects the kernel mapping behind qmpc_solve (1 Riccati kernel alone, 2 = default for
+    fp64 and N <= 21: Riccati screening + dense condensed kernel).  Both mappings land on the oracle's minimiser."""
+    B, N, M = 67, 20, 20                      # odd batch: partial CTA paths
     dt = 1.0 / N
     quad = orc.quad_hummingbird()
     gp = make_gp(M)
     sc = random_ocp_batch(B, N, dt, quad, gp, seed=7, amp_choices=(8.0, 2.0, 0.5))
-    x, u, cost, st, it = _solve_batch(sc, B, N, gp)
+    x, u, cost, st, it = _solve_batch(sc, B, N, gp, solver_variant=variant)
     xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
     assert (st == 0).all(), st
     assert u_rel(u, uo) < TOL_U64 and x_rel(x, xo) < TOL_X64

@@ -10,8 +10,9 @@ from emu import emu
 
 
 # the dense kernel works on the condensed Hessian (cond ~1e6..1e7): ~1e-9 relative instead of ~1e-12; north_star asks 1e-6
-TOL = {0: 1e-9, 1: 1e-9, 2: 2e-8, 3: 2e-8}
-VARIANTS = pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["warp_per_ocp", "two_ocps_per_warp", "screen_plus_dense", "screen2_plus_dense"])
+TOL = {1: 1e-9, 2: 2e-8}
+# qmpc_config.solver_variant: 1 = Riccati kernel alone (one OCP per warp), 2 = Riccati screening launch + dense launch
+VARIANTS = pytest.mark.parametrize("variant", [1, 2], ids=["warp_per_ocp", "screen_plus_dense"])
 
 
 @VARIANTS
@@ -36,7 +37,7 @@ def test_emulated_solve_matches_oracle(N, use_gp, variant):
 
 @VARIANTS
 def test_emulated_solve_fp32_within_1e4(variant):
-    if variant >= 2:
+    if variant == 2:
         pytest.skip("fp32 handles use the Riccati kernel alone: the condensed Hessian (cond ~1e7) is an fp64-only formulation")
     B, N = 2, 10
     dt = 1.0 / N
@@ -90,17 +91,15 @@ def test_emulated_warm_start_from_previous_active_set(variant):
     assert u_rel(u2, uo) < TOL[variant] and x_rel(x2, xo) < TOL[variant]
 
 
-def test_emulated_dense_kernel_continues_the_screening_rounds(monkeypatch):
+def test_emulated_dense_kernel_continues_the_screening_rounds():
     """screening limited to one round, the dense kernel continues with active-set rounds from the handed-over guess
-    (QMPC_SCREEN_ROUNDS=1, QMPC_DENSE_WARM_ROUNDS=8) and falls back to its IPM: same exact minimiser"""
-    monkeypatch.setenv("QMPC_SCREEN_ROUNDS", "1")
-    monkeypatch.setenv("QMPC_DENSE_WARM_ROUNDS", "8")
+    (qmpc_config screen_rounds=1, dense_warm_rounds=8) and falls back to its IPM: same exact minimiser"""
     B, N = 4, 20
     dt = 1.0 / N
     quad = orc.quad_hummingbird()
     gp = make_gp(20)
     sc = random_ocp_batch(B, N, dt, quad, gp, seed=3, amp_choices=(8.0, 2.0))
-    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta, screen_rounds=1, dense_warm_rounds=8)
     xe, ue = sc["xit"].copy(), sc["uit"].copy()
     r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=2)
     sc2 = dict(sc)
@@ -114,7 +113,7 @@ def test_emulated_dense_kernel_continues_the_screening_rounds(monkeypatch):
     print("dense continuation: ipm iters", r2["iters"], "rounds", r2["rounds"])
 
 
-@pytest.mark.parametrize("variant", [0, 2], ids=["warp_per_ocp", "screen_plus_dense"])
+@VARIANTS
 def test_emulated_breakdown_is_contained(variant):
     """a non-finite iterate in ONE vehicle: that vehicle reports status 2, keeps its iterate, holds its (clipped) previous
     first control and forgets its active set; its neighbours (same warp / same CTA loop) are solved as if it were not there"""
@@ -133,3 +132,29 @@ def test_emulated_breakdown_is_contained(variant):
     assert np.isnan(xe[1, 4, 8]) and np.array_equal(ue[1, 0], [0.3, 1.7, -0.2, 0.5])       # iterate untouched
     for b in (0, 2):
         assert np.abs(ue[b] - uo[b]).max() < TOL[variant] and np.abs(xe[b] - xo[b]).max() < 10 * TOL[variant]
+
+
+@VARIANTS
+def test_emulated_cold_handle_never_uses_the_remembered_active_set(variant):
+    """warm_start_rounds < 0: neither the screening nor the dense kernel may look at the active set of the previous solve
+    (the dense kernel used to run up to 8 warm rounds anyway).  Every OCP takes the cold IPM: iters > 0, and
+    the answer is the same exact minimiser."""
+    B, N = 3, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(20)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=3, amp_choices=(8.0, 2.0))
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta, warm_start_rounds=-1)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=variant)
+    assert (r1["iters"] > 0).all()
+    sc2 = dict(sc)
+    sc2["x0"] = sc["x0"] + 0.002 * np.random.default_rng(1).standard_normal(sc["x0"].shape)
+    sc2["xit"], sc2["uit"] = xe.copy(), ue.copy()
+    xo, uo, _, _ = oracle_solve_batch(sc2, quad, dt, N, gp)
+    x2, u2 = xe.copy(), ue.copy()
+    r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=r1["act"].copy(), variant=variant)
+    assert (r2["status"] == 0).all() and (r2["iters"] > 0).all(), (r2["iters"], r2["rounds"])
+    assert u_rel(u2, uo) < TOL[variant] and x_rel(x2, xo) < TOL[variant]
+    if variant == 2:
+        assert r2["hard"] == B          # nothing was screened
