@@ -75,6 +75,11 @@ typedef struct {
     int bail_changed;      /* a warm round that still moves more inputs than this ends the attempt: 0 -> never */
     int final_rollout;     /* >0 -> always re-roll the horizon at the end of a solve (A/B knob): 0 -> reuse the last sweep */
     int dense_grid;        /* persistent CTAs of the dense launch: 0 -> min(resident CTAs, max(32, B/6)) */
+    int screen_rounds_busy; /* round limit of the screening launch in a BUSY step: 0 -> 8, <0 -> same as screen_rounds.  A step
+                              is busy when the previous step left more than screen_busy_pct % of the vehicles unsettled
+                              after screen_rounds rounds (start-up transients, aggressive references): the dense launch
+                              would need several waves then, and a Riccati round is cheaper than the dense condensing */
+    int screen_busy_pct;   /* 0 -> 20 */
 } qmpc_config;
 
 const char *qmpc_last_error(void);
@@ -97,6 +102,10 @@ int qmpc_set_x0(qmpc_handle_t h, const double *x0, void *stream);
 int qmpc_set_params(qmpc_handle_t h, const double *mu, const double *Kx_inv, void *stream);
 /* the same, when alpha [B][3][M] is already available (qrgp_get_alpha) */
 int qmpc_set_alpha(qmpc_handle_t h, const double *alpha, void *stream);
+/* the same without a copy: later solves read alpha from the caller's device buffer (stride = doubles between vehicles:
+ * 3*M, or 0 when one shared model serves every vehicle); NULL returns to the handle's own storage.  Host-side switch,
+ * takes effect for solves queued afterwards (used by the shared-swarm mode to double-buffer the model). */
+int qmpc_bind_alpha(qmpc_handle_t h, const double *alpha, int stride);
 /* persistent SQP iterate (acados keeps it inside the capsule; zero after create):
  * x [B][N+1][13], u [B][N][4] */
 int qmpc_set_iterate(qmpc_handle_t h, const double *x, const double *u, void *stream);
@@ -119,6 +128,10 @@ int qmpc_get_fail_streak(qmpc_handle_t h, int *streak /*[B]*/, void *stream);
 int qmpc_get_refine_rounds(qmpc_handle_t h, int *rounds /*[B]*/, void *stream);
 /* OCPs the screening launch of the last solve handed to the dense launch (host value; synchronises `stream`) */
 int qmpc_get_hard_count(qmpc_handle_t h, int *count_host, void *stream);
+/* active sets remembered for the warm start, device u8 [B][4N]: 0 free, 1 at lbu, 2 at ubu, 255 unknown.  They steer
+ * which path a solve takes (warm rounds / IPM), never its answer; exposed for replaying a solve elsewhere. */
+int qmpc_get_active_set(qmpc_handle_t h, unsigned char *act, void *stream);
+int qmpc_set_active_set(qmpc_handle_t h, const unsigned char *act, void *stream);
 /* forget the active sets remembered for the warm start (the next solve starts from the cold IPM) */
 int qmpc_reset_warm_start(qmpc_handle_t h, void *stream);
 /* sum over vehicles of IPM iterations of the last solve (host value; synchronises `stream`) */
@@ -134,6 +147,14 @@ int qmpc_compute_a_drag(int B, const double *x_now, const double *x_pred, double
                         double *v_body, double *a_drag, void *stream);
 /* utils.get_reference_chunk (utils.py:897-931): traj [B][K][13], idx (same for all) -> chunk [B][N][13] */
 int qmpc_reference_chunk(int B, int K, const double *traj, int idx, int N, int skip, double *chunk, void *stream);
+/* the same chunk without a stored trajectory: the reference generators evaluated on the device at the sample times
+ * (row * dt, rows chosen like get_reference_chunk, rows past K-1 repeat row K-1).  params device [B][QMPC_REFGEN_NPAR]:
+ * kind 0 sum of three sinusoids per axis (amp[3][3], f[3][3] Hz, phase[3][3], scale, p0[3], z0), kind 1 lemniscate
+ * (phase, yaw, w, a, z0, p0x, p0y, ramp time), kind 2 accelerating circle of TrajectoryGenerator.py:41-74 (radius, v_max,
+ * n samples, start[3], csv-rounding flag).  q = (1,0,0,0), r = 0 as TrajectoryGenerator.load_trajectory leaves them. */
+#define QMPC_REFGEN_NPAR 32
+int qmpc_reference_generate(int kind, int B, const double *params, int K, int idx, int N, int skip, double dt,
+                            double *chunk, void *stream);
 /* Quadrotor3D.update repeated over one control period (quad.py:234-277, execute_trajectory.py:232-243):
  * plant[4] = aero_drag, rotor_drag xyz (host); x [B][13] in/out; u [B][4]; n_sub sub-steps of sim_dt */
 int qmpc_plant_period(const double *quad /*host[20]*/, const double *plant /*host[4]*/, int B, double *x,

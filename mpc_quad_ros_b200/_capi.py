@@ -22,6 +22,7 @@ class QmpcConfig(C.Structure):
         ("gp_X", C.POINTER(C.c_double)),
         ("solver_variant", C.c_int), ("reset_on_fail", C.c_int), ("screen_rounds", C.c_int), ("dense_warm_rounds", C.c_int),
         ("bail_round", C.c_int), ("bail_changed", C.c_int), ("final_rollout", C.c_int), ("dense_grid", C.c_int),
+        ("screen_rounds_busy", C.c_int), ("screen_busy_pct", C.c_int),
     ]
 
 

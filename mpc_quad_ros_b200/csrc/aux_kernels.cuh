@@ -146,6 +146,85 @@ __global__ void reference_chunk_kernel(int B, int K, const double* __restrict__ 
     chunk[t] = traj[((size_t)b * K + row) * NX + c];
 }
 
+// ---- reference generation on the device: the chunk get_reference_chunk (utils.py:897-931) would cut out of
+// a trajectory sampled at t = row * dt is evaluated analytically instead, so a closed loop never uploads references.
+// q = (1,0,0,0) and r = 0 as in TrajectoryGenerator.load_trajectory (TrajectoryGenerator.py:237-238).
+// par[b][REFGEN_NPAR], by kind:
+//   0 sum of three sinusoids per axis (BASELINE config 2): amp[3][3], f[3][3] (Hz), phase[3][3], scale, p0[3], z0
+//   1 lemniscate (config 5): phase, yaw, w, a, z0, p0x, p0y, ramp time T (angular rate ramps 0 -> w over T)
+//   2 accelerating circle (config 1, TrajectoryGenerator.sample_circle_trajectory_accelerating :41-74): radius, v_max,
+//     n (samples of the whole trajectory), start[3], csv flag (values rounded to 6 decimals, the reference's '%.6f' file)
+constexpr int REFGEN_NPAR = 32;
+
+__device__ __forceinline__ double csv6(double v) { return rint(v * 1e6) / 1e6; }
+
+__global__ void reference_generate_kernel(int kind, int B, const double* __restrict__ par, int K, int idx, int N, int skip,
+                                          double dt, double* __restrict__ chunk)
+{
+    const int t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= B * N) return;
+    const int k = t_ % N, b = t_ / N;
+    const int left = K - idx;
+    int row;                                                   // same row rule as reference_chunk_kernel
+    if (left > N * skip) row = idx + k * skip;
+    else if (left > skip - 1) {
+        const int n_left = (left + skip - 1) / skip;
+        row = k < n_left ? idx + k * skip : K - 1;
+    } else row = K - 1;
+    const double* q = par + (size_t)b * REFGEN_NPAR;
+    const double t = row * dt;
+    const double two_pi = 6.283185307179586;
+    double p[3], v[3];
+    if (kind == 0) {
+        const double s = q[27];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double ps = 0, vs = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double amp = q[a * 3 + j], f = q[9 + a * 3 + j], arg = two_pi * f * t + q[18 + a * 3 + j];
+                double sn, cs;
+                sincos(arg, &sn, &cs);
+                ps += amp * sn;
+                vs += amp * two_pi * f * cs;
+            }
+            p[a] = ps * s - q[28 + a];
+            v[a] = vs * s;
+        }
+        p[2] += q[31];
+    } else if (kind == 1) {
+        const double ph = q[0], yaw = q[1], w = q[2], a = q[3], T = q[7];
+        const double th = ph + w * (t < T ? t * t / (2.0 * T) : t - 0.5 * T);
+        const double dth = w * (t < T ? t / T : 1.0);
+        double sth, cth, sy, cy;
+        sincos(th, &sth, &cth);
+        sincos(yaw, &sy, &cy);
+        const double px = a * sth, py = a * sth * cth, vx = a * cth * dth, vy = a * cos(2.0 * th) * dth;
+        p[0] = cy * px - sy * py - q[5]; p[1] = sy * px + cy * py - q[6]; p[2] = q[4];
+        v[0] = cy * vx - sy * vy; v[1] = sy * vx + cy * vy; v[2] = 0.0;
+    } else {
+        const double radius = q[0], w_max = q[1] / q[0], n = q[2];
+        // w_m = w_max (sin(pi k_m + 3 pi / 4) + 1) / 2 with k_m = 2 (m + 1) / n - 1; phi_row = dt * sum_{m <= row} w_m in closed form
+        const double d = two_pi / n, a0 = 0.5 * two_pi * (2.0 / n - 1.0) + 0.75 * 0.5 * two_pi;
+        const double S = sin(a0 + 0.5 * row * d) * sin(0.5 * (row + 1) * d) / sin(0.5 * d);
+        const double phi = w_max * dt * 0.5 * ((row + 1) + S);
+        const double w = w_max * 0.5 * (sin(a0 + row * d) + 1.0);
+        double sp, cp;
+        sincos(phi, &sp, &cp);
+        p[0] = radius * cp - radius + q[3]; p[1] = radius * sp + q[4]; p[2] = q[5];
+        v[0] = -radius * w * sp; v[1] = radius * w * cp; v[2] = 0.0;
+        if (q[6] != 0.0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { p[a] = csv6(p[a]); v[a] = csv6(v[a]); }
+        }
+    }
+    double* o = chunk + (size_t)t_ * NX;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    o[3] = 1.0; o[4] = 0.0; o[5] = 0.0; o[6] = 0.0;
+    o[7] = v[0]; o[8] = v[1]; o[9] = v[2];
+    o[10] = 0.0; o[11] = 0.0; o[12] = 0.0;
+}
+
 // Quadrotor3D.update (quad.py:234-277,305-381): RK4 of the nominal model + aero/rotor drag, inputs clipped to [0,1]
 struct PlantParams { double aero, rotor[3], mass; };
 

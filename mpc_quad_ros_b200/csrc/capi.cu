@@ -72,6 +72,7 @@ struct qmpc_solver {
     long long* timeline = nullptr;    // [B][2] per-OCP start/end stamps when enabled
     int variant = 2;                  // host_params.h solver_variant(): 1 Riccati kernel alone, 2 Riccati screening + dense kernel
     bool reset_failed = true;         // qmpc_config::reset_on_fail
+    int parity = 0;                   // which of the two unsettled counters this solve writes
     const double* x0_src = nullptr;   // where the next solve reads x0 / alpha from (own buffers or bound ones)
     const double* alpha_src = nullptr;
     int alpha_stride = 0;
@@ -148,15 +149,15 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     CU_TRY(cudaMemset(h->fail_streak, 0, B * 4));
     if (M) CU_TRY(cudaMemcpy(h->gpX, cfg->gp_X, 3 * M * 8, cudaMemcpyHostToDevice));
     h->x0_src = h->x0; h->alpha_src = h->alpha; h->alpha_stride = 3 * (int)M;
-    const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N) * 8 + 16384, smem32 = smem64 / 2 + 8192;
+    const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N, true, true) * 8, smem32 = (size_t)IPM_WARPS * ipm_smem_reals((int)N, true, false) * 4;
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<double, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     CU_TRY(cudaFuncSetAttribute(qmpc_ipm_kernel<float, IPM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
     h->variant = solver_variant(h->cfg, DN_MAX_N);
     if (h->variant == 2) {
         const int smemd = dense_layout((int)N).total * 8;
-        CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->hard), (B + 1) * sizeof(int)));
-        CU_TRY(cudaMemset(h->hard, 0, (B + 1) * sizeof(int)));
+        CU_TRY(cudaMalloc(reinterpret_cast<void**>(&h->hard), (B + 4) * sizeof(int)));      // list, count, work-queue counter, unsettled x2
+        CU_TRY(cudaMemset(h->hard, 0, (B + 4) * sizeof(int)));
         CU_TRY(cudaFuncSetAttribute(qmpc_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
         int per_sm = 0, sms = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<double>, DN_THREADS, smemd));
@@ -235,6 +236,16 @@ int qmpc_set_alpha(qmpc_handle_t h, const double* alpha, void* stream)
     return copy_dd(h->alpha, alpha, (size_t)h->cfg.batch * 3 * h->cfg.n_basis * 8, stream);
 }
 
+int qmpc_bind_alpha(qmpc_handle_t h, const double* alpha, int stride)
+{
+    if (!h) return fail(QMPC_ERR_ARG, "null handle");
+    if (h->cfg.n_basis == 0) return fail(QMPC_ERR_ARG, "solver was created without an RGP model (n_basis == 0)");
+    if (alpha && stride != 0 && stride != 3 * h->cfg.n_basis) return fail(QMPC_ERR_ARG, "stride must be 0 (one shared model) or 3*n_basis");
+    h->alpha_src = alpha ? alpha : h->alpha;
+    h->alpha_stride = alpha ? stride : 3 * h->cfg.n_basis;
+    return QMPC_OK;
+}
+
 int qmpc_set_iterate(qmpc_handle_t h, const double* x, const double* u, void* stream)
 {
     if (!h) return fail(QMPC_ERR_ARG, "null handle");
@@ -290,8 +301,12 @@ static int solve_impl(qmpc_solver* h, void* stream)
         // With the warm start off there is nothing to screen: the dense kernel takes every OCP from its cold IPM.
         fill_screen_args(h->cfg, ia);
         const bool screen = ia.warm_rounds > 0;
+        CU_TRY(cudaMemsetAsync(h->hard + B, 0, 2 * sizeof(int), S(stream)));
         if (screen) {
-            CU_TRY(cudaMemsetAsync(h->hard + B, 0, sizeof(int), S(stream)));
+            // unsettled-after-screen_rounds counters of this and of the previous solve (ping-pong, no device copy)
+            h->parity ^= 1;
+            ia.unsettled_cur = h->hard + B + 2 + h->parity; ia.unsettled_prev = h->hard + B + 2 + (h->parity ^ 1);
+            CU_TRY(cudaMemsetAsync(ia.unsettled_cur, 0, sizeof(int), S(stream)));
             ia.hard_list = h->hard; ia.hard_count = h->hard + B;
             const size_t smem_s = (size_t)IPM_WARPS * ia.smem_per_warp * sizeof(real);
             qmpc_ipm_kernel<real, IPM_WARPS><<<cdiv(B, IPM_WARPS), IPM_WARPS * 32, smem_s, S(stream)>>>(ia);
@@ -306,6 +321,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
         DenseArgs<real> dn;
         dn.b = ia;
         dn.hard_list = screen ? h->hard : nullptr; dn.hard_count = screen ? h->hard + B : nullptr;
+        dn.next_item = h->hard + B + 1;
         if constexpr (sizeof(real) == 8)
             qmpc_dense_kernel<real><<<h->dense_grid, DN_THREADS, dense_layout(N).total * sizeof(real), S(stream)>>>(dn);
     } else {
@@ -371,6 +387,16 @@ int qmpc_get_hard_count(qmpc_handle_t h, int* count_host, void* stream)
     CU_TRY(cudaStreamSynchronize(S(stream)));
     return QMPC_OK;
 }
+int qmpc_get_active_set(qmpc_handle_t h, unsigned char* act, void* stream)
+{
+    if (!h || !act) return fail(QMPC_ERR_ARG, "null argument");
+    return copy_dd(act, h->act, (size_t)h->cfg.batch * h->cfg.n_nodes * NU, stream);
+}
+int qmpc_set_active_set(qmpc_handle_t h, const unsigned char* act, void* stream)
+{
+    if (!h || !act) return fail(QMPC_ERR_ARG, "null argument");
+    return copy_dd(h->act, act, (size_t)h->cfg.batch * h->cfg.n_nodes * NU, stream);
+}
 int qmpc_reset_warm_start(qmpc_handle_t h, void* stream)
 {
     if (!h) return fail(QMPC_ERR_ARG, "null handle");
@@ -424,6 +450,16 @@ int qmpc_reference_chunk(int B, int K, const double* traj, int idx, int N, int s
 {
     if (!traj || !chunk || B < 1 || K < 1 || N < 1 || skip < 1 || idx < 0) return fail(QMPC_ERR_ARG, "bad argument");
     reference_chunk_kernel<<<cdiv((long long)B * N * NX, 256), 256, 0, S(stream)>>>(B, K, traj, idx, N, skip, chunk);
+    LAUNCH_CHECK();
+    return QMPC_OK;
+}
+
+int qmpc_reference_generate(int kind, int B, const double* params, int K, int idx, int N, int skip, double dt, double* chunk,
+                            void* stream)
+{
+    if (!params || !chunk || B < 1 || K < 1 || N < 1 || skip < 1 || idx < 0 || kind < 0 || kind > 2 || !(dt > 0))
+        return fail(QMPC_ERR_ARG, "bad argument");
+    reference_generate_kernel<<<cdiv((long long)B * N, 128), 128, 0, S(stream)>>>(kind, B, params, K, idx, N, skip, dt, chunk);
     LAUNCH_CHECK();
     return QMPC_OK;
 }
@@ -646,12 +682,14 @@ int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const doubl
     set_reference_kernel<<<cdiv((long long)B * N * NY, 256), 256, 0, S(stream)>>>(B, N, x_ref, nullptr, 0.16, h->yref, h->yref_e);
     LAUNCH_CHECK();
     h->x0_src = x_now;
+    const double* bound_alpha = h->alpha_src;
+    const int bound_stride = h->alpha_stride;
     // the reference's solver parameters are whatever was last pushed: zeros (or qmpc_set_params/alpha) until the first
     // regress of this model (quad_opt.py:101,402-404)
     if (g && g->pushed) { h->alpha_src = g->alpha; h->alpha_stride = g->B == 1 ? 0 : 3 * g->M; }
     int rc = qmpc_solve(h, stream);
     h->x0_src = h->x0;
-    if (g) { h->alpha_src = h->alpha; h->alpha_stride = 3 * h->cfg.n_basis; }
+    h->alpha_src = bound_alpha; h->alpha_stride = bound_stride;
     if (rc) return rc;
     const bool per_vehicle = g && g->B == B;
     double* xt = per_vehicle ? g->xt : h->xt;

@@ -55,6 +55,68 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 #endif
 }
 
+// ---- TMA bulk copy global -> shared memory with an mbarrier (cp.async.bulk, SASS UBLKCP): one thread issues the copy,
+// every consumer waits on the barrier's phase.  In the host emulation the issuing thread copies synchronously and the
+// wait is a block / warp barrier (bulk_wait_block / bulk_wait_warp).
+#ifndef QMPC_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// order this thread's earlier generic-proxy accesses to shared memory before async-proxy (TMA) writes to it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one copy of `bytes` (multiple of 16, both addresses 16-byte aligned) that completes on `bar` (byte count announced
+// with mbar_expect beforehand)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QMPC_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QMPC_MBAR_DONE;\n"
+        "bra QMPC_MBAR_WAIT;\n"
+        "QMPC_MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long*, int) {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void mbar_expect(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
+#endif
+// consumers' side: every thread of the CTA (resp. lane of the warp) calls this after the issuing thread has issued
+__device__ __forceinline__ void bulk_wait_block(unsigned long long* bar, unsigned parity)
+{
+#ifdef QMPC_EMU
+    (void)bar; (void)parity;
+    __syncthreads();
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+__device__ __forceinline__ void bulk_wait_warp(unsigned long long* bar, unsigned parity)
+{
+#ifdef QMPC_EMU
+    (void)bar; (void)parity;
+    __syncwarp();
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 template <typename real> __device__ __forceinline__ real rrsqrt(real x);
 #ifdef QMPC_EMU
 template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return 1.0 / sqrt(x); }

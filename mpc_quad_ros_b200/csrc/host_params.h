@@ -28,8 +28,16 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
 }
 
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
-inline int ipm_smem_reals(int N) { return (SM_VEC + SM_NVEC * 4 * N + (N + 1) * 13 + 9) & ~1; }
-inline int ipm_smem_reals_screen(int N) { return (SM_VEC + 7 * 4 * N + (N + 1) * 13 + 9) & ~1; }   // screening mode layout
+// per-warp shared memory of the Riccati kernel (reals): working set, then (fp64 QMPC_RING builds) the tile ring and one
+// 8-byte mbarrier per slot.  `full`: the IPM layout (13 vectors); otherwise the screening layout (7 vectors).
+inline int ipm_ring_off(int N, bool full) { return (SM_VEC + (full ? SM_NVEC : 7) * 4 * N + (N + 1) * 13 + 9) & ~1; }
+inline int ipm_smem_reals(int N, bool full, bool fp64)
+{
+    const int ring = fp64 ? QMPC_RING : 0;
+    const int hist = fp64 ? HIST_REALS<double>() : HIST_REALS<float>();
+    const int mbar = fp64 ? ring : 2 * ring;
+    return (ipm_ring_off(N, full) + hist + ring * WT + mbar + 1) & ~1;
+}
 
 template <typename real>
 inline void fill_lin_args(const qmpc_config& c, LinArgs<real>& a)
@@ -54,17 +62,27 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.max_iter_failed = a.max_iter < 20 ? a.max_iter : 20;
     a.fail_streak = nullptr;
     a.mu_switch = real(c.ipm_mu_switch > 0 ? c.ipm_mu_switch : 1e-4);
-    a.lam0_scale = real(0.01); a.lam0_min = real(0.1); a.lam0_max = real(100.0);
+    // initial multipliers of a cold IPM: clip(0.02 * mean|dJ/du(box centre)|, 0.1, 1e5).  The upper clip used to be 100: a vehicle
+    // 30-80 m off its reference (gradients of 1e3-1e4, 75 of 80 inputs saturated) then spent 25-45 iterations growing the
+    // multipliers, 8-15 now; ordinary problems are unaffected (profiles/r02_lam0_sweep.txt)
+    a.lam0_scale = real(0.02); a.lam0_min = real(0.1); a.lam0_max = real(1e5);
+#ifdef QMPC_EMU       // tuning hook of the test-only emulation build (scripts/replay_hard.py)
+    if (getenv("EMU_LAM0_SCALE")) a.lam0_scale = real(atof(getenv("EMU_LAM0_SCALE")));
+    if (getenv("EMU_LAM0_MAX")) a.lam0_max = real(atof(getenv("EMU_LAM0_MAX")));
+#endif
     a.refine_gtol = real(f64 ? 1e-12 : 1e-5);
     a.resfac_final = real(f64 ? 1e-9 : 1e-3);
     a.max_refine = c.refine_max_rounds < 0 ? 0 : (c.refine_max_rounds == 0 ? (f64 ? 20 : 10) : c.refine_max_rounds);
     a.post_bail = f64 ? 0 : 1;
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
-    a.smem_per_warp = ipm_smem_reals(c.n_nodes);
+    a.smem_per_warp = ipm_smem_reals(c.n_nodes, true, f64);
+    a.ring_off = ipm_ring_off(c.n_nodes, true);
     a.bail_round = c.bail_round > 0 ? c.bail_round : 2;
     a.bail_changed = c.bail_changed > 0 ? c.bail_changed : (1 << 20);
     a.final_rollout = c.final_rollout > 0 ? 1 : 0;
     a.dense_warm_rounds = 0;
+    a.warm_rounds_busy = 0; a.bail_round_busy = a.bail_round; a.busy_threshold = 1 << 30; a.skip_screen_iters = 0;
+    a.unsettled_prev = nullptr; a.unsettled_cur = nullptr;
     a.timeline = nullptr; a.hard_list = nullptr; a.hard_count = nullptr;
 }
 
@@ -85,8 +103,16 @@ inline void fill_screen_args(const qmpc_config& c, IpmArgs<real>& a)
     const int screen = c.screen_rounds > 0 ? c.screen_rounds : 3;
     const int dense_warm = c.dense_warm_rounds < 0 ? 0 : (c.dense_warm_rounds == 0 ? 8 : c.dense_warm_rounds);
     a.dense_warm_rounds = a.warm_rounds > 0 ? dense_warm : 0;
-    if (a.warm_rounds > screen) a.warm_rounds = screen;
-    a.smem_per_warp = ipm_smem_reals_screen(c.n_nodes);
+    if (a.warm_rounds > 0) {
+        a.warm_rounds = screen;
+        a.warm_rounds_busy = c.screen_rounds_busy < 0 ? 0 : (c.screen_rounds_busy == 0 ? 8 : c.screen_rounds_busy);
+        a.bail_round_busy = a.bail_round > 3 ? a.bail_round : 3;
+        const int pct = c.screen_busy_pct > 0 ? c.screen_busy_pct : 20;
+        a.busy_threshold = (int)((long long)c.batch * pct / 100);
+        a.skip_screen_iters = 12;
+    }
+    a.smem_per_warp = ipm_smem_reals(c.n_nodes, false, sizeof(real) == 8);
+    a.ring_off = ipm_ring_off(c.n_nodes, false);
 }
 
 }  // namespace qmpc

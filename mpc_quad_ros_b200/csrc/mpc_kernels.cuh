@@ -9,7 +9,7 @@
 //       src/_acados_ocp.json:2082-2110).  Full step, un-shifted persistent iterate, objective at the new
 //       iterate.
 //
-// Per-stage tile written by K1 and streamed by K2 (HBM/L2, `real`):   W[13 rows][16 cols]
+// Per-stage tile written by K1 and streamed by K2 (HBM/L2, `real`):   W[13 rows][16 cols], row stride WR
 //   cols 0..3  = B = dPhi/du            cols 4..13 = dPhi/dx_s for s = 3..12 (q,v,r)
 //   col 14     = b = Phi(x_k,u_k) - x_{k+1}  (QP in increments)        col 15 = q = dt*W_x (x_k - xref_k)
 // The three position columns of A are unit vectors (f does not depend on p) and are never stored.
@@ -20,7 +20,14 @@
 namespace qmpc {
 
 constexpr int QMPC_STATUS_OK_ = 0, QMPC_STATUS_MAXITER_ = 1, QMPC_STATUS_NAN_ = 2;
-constexpr int WT = 13 * 16;  // reals per stage tile
+#ifndef QMPC_WR
+#define QMPC_WR 18               // row stride of a stage tile in reals (18: rows 144 B apart, bank-conflict-free row reads from shared memory)
+#endif
+#ifndef QMPC_RING
+#define QMPC_RING 2              // Riccati kernel: stage tiles staged through a shared-memory ring of this many slots by TMA bulk copies (0: read from L2/L1)
+#endif
+constexpr int WR = QMPC_WR;
+constexpr int WT = 13 * WR;  // reals per stage tile
 constexpr int FAC = 72;      // reals per stage factor record: Lx[13][4], lg[4], Lam[10], lgc[4], pad[2]
 
 template <typename real>
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real> a)
     }
     real* Wt = a.W + (size_t)node * WT;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) Wt[i * 16 + j] = accd[i];
+    for (int i = 0; i < NX; ++i) Wt[i * WR + j] = accd[i];
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -132,11 +139,18 @@ struct IpmArgs {
     int max_refine;                // refinement rounds after the IPM; 0 = pure IPM down to mu_tol
     int warm_rounds;               // refinement rounds tried FIRST from the previous solve's active set; 0 = off
     int dense_warm_rounds;         // dense kernel: active-set rounds from the handed-over guess before the IPM; 0 = IPM first
+    int warm_rounds_busy;          // screening mode: round limit of a busy step (see unsettled_prev); 0 = warm_rounds
+    int bail_round_busy;           // bail_round of a busy step
+    int skip_screen_iters;         // screening mode: previous-solve IPM iterations from which an OCP skips the rounds (0 = never)
+    int busy_threshold;            // a step is busy when the previous step left more than this many OCPs unsettled after warm_rounds
+    const int* unsettled_prev;     // device counters (previous / this step) of OCPs not settled after warm_rounds rounds, or null
+    int* unsettled_cur;
     int bail_round;                // rounds (0-based) from which a non-contracting change count ends the attempt (default 2)
     int bail_changed;              // a round that still moves more inputs than this ends the attempt at once (default: never)
     int final_rollout;             // 1: always roll the horizon out at the end (A/B knob)
     int post_bail;                 // 1: the rounds after the IPM may give up early too (fp32: rounding noise can keep them busy)
     int smem_per_warp;             // reals
+    int ring_off;                  // offset (reals) of the tile ring + its mbarriers inside the per-warp block (QMPC_RING builds)
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
     const double* yref_e;          // [B][13]
@@ -245,6 +259,34 @@ struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal
     }
 };
 
+// ---- cycle detection of the primal-dual active-set rounds: 64-bit fingerprint of an active set (sum over the inputs of
+// a per-(input, state) odd multiplier; lanes add their elements, warp_sum completes it) and the last few fingerprints.
+template <typename real>
+__device__ __forceinline__ unsigned long long active_set_term(int e, real f)
+{
+    const unsigned long long k = (unsigned long long)(e + 1) * 0x9E3779B97F4A7C15ull;
+    return f == real(0) ? 0ull : (f == real(1) ? (k | 1ull) : (k * 0xC2B2AE3D27D4EB4Full) | 1ull);
+}
+struct ActiveSetHistory {      // storage in shared memory (registers are the scarce resource of both solver kernels)
+    static constexpr int DEPTH = 6;
+    unsigned long long* h;
+    int n;
+    __device__ __forceinline__ void init(void* storage) { h = reinterpret_cast<unsigned long long*>(storage); n = 0; }
+    __device__ __forceinline__ void clear() { n = 0; }
+    // warp-collective: every lane passes the same fingerprint; returns whether it was met before, then records it
+    __device__ __forceinline__ bool seen_then_push(unsigned long long fp, int lane)
+    {
+        bool hit = false;
+        const int m = n < DEPTH ? n : DEPTH;
+        for (int i = 0; i < m; ++i) hit = hit || h[i] == fp;
+        __syncwarp();
+        if (lane == 0) h[n % DEPTH] = fp;
+        __syncwarp();
+        ++n;
+        return hit;
+    }
+};
+
 template <typename real>
 __device__ __forceinline__ real dot4(const real* a, const real* b)
 {
@@ -268,6 +310,8 @@ constexpr int SM_CS = 328;     // 32  Muu(16) Mpu(12) gu(4)
 constexpr int SM_VEC = 360;    // 13 vectors of 4N, then the state trajectory (N+1) x 13 of the refinement
 constexpr int SM_NVEC = 13;
 
+template <typename real> __host__ __device__ constexpr int HIST_REALS() { return 64 / (int)sizeof(real); }   // 64 bytes
+
 template <typename real>
 struct WarpCtx {
     const IpmArgs<real>& a;
@@ -281,19 +325,64 @@ struct WarpCtx {
     const double *x0, *yref, *yref_e;
     double *xit, *uit;
 
-    __device__ __forceinline__ void load_col(int k, real* w) const
+    // ---- stage tiles.  RING (fp64 builds with QMPC_RING > 0): a sweep streams its tiles through RING shared-memory slots;
+    // lane 0 issues one TMA bulk copy per stage (cp.async.bulk + mbarrier, RING - 1 stages ahead of the compute), the warp
+    // waits on the slot's barrier and reads the tile with LDS.  Otherwise the tile is read in place (L2/L1, __ldg).
+    static constexpr int RING = (sizeof(real) == 8) ? QMPC_RING : 0;
+    void* hist_store;                // 6 x 8 bytes: active-set fingerprints of the running attempt (cycle detection)
+    real* ring;                      // RING slots of WT reals
+    unsigned long long* rbar;        // one mbarrier per slot
+    unsigned rphase;                 // bit s: parity of the next completion of slot s
+
+    __device__ __forceinline__ static real tld(const real* p) { return RING ? *p : __ldg(p); }
+    __device__ __forceinline__ static void tld2(const real* p, real& x, real& y) { if (RING) ld2(p, x, y); else ldg2(p, x, y); }
+
+    __device__ __forceinline__ void ring_issue(int slot, int k) const
     {
-        const real* t = Wv + (size_t)k * WT + j;
+        if (lane == 0) {
+            mbar_expect(rbar + slot, (unsigned)(WT * sizeof(real)));
+            bulk_g2s(ring + slot * WT, Wv + (size_t)k * WT, (unsigned)(WT * sizeof(real)), rbar + slot);
+        }
+    }
+    // start of a sweep over stages k0, k0 + dir, ...: fill the ring
+    __device__ __forceinline__ void sweep_begin(int k0, int dir) const
+    {
+        if (RING) {
+            __syncwarp();            // the slots' last readers are done
 #pragma unroll
-        for (int i = 0; i < NX; ++i) w[i] = __ldg(t + i * 16);
+            for (int s = 0; s < RING; ++s) { const int k = k0 + s * dir; if (k >= 0 && k < N) ring_issue(s, k); }
+        }
+    }
+    // tile of the i-th stage of the sweep (stage index k)
+    __device__ __forceinline__ const real* tile_at(int i, int k)
+    {
+        if (RING) {
+            const int s = i % (RING ? RING : 1);
+            bulk_wait_warp(rbar + s, (rphase >> s) & 1u);
+            rphase ^= 1u << s;
+            return ring + s * WT;
+        }
+        return Wv + (size_t)k * WT;
+    }
+    // call after a warp barrier that follows the last read of the i-th tile: refills its slot with stage knext
+    __device__ __forceinline__ void tile_done(int i, int knext) const
+    {
+        if (RING) { if (knext >= 0 && knext < N) ring_issue(i % (RING ? RING : 1), knext); }
+    }
+
+    __device__ __forceinline__ void load_col(const real* tile, real* w) const
+    {
+        const real* t = tile + j;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) w[i] = tld(t + i * WR);
     }
 
     // L1 prefetch of the tile (13 lines) and factor record (<= 6 lines) of the stage the sweep visits next
     __device__ __forceinline__ void prefetch_stage(int k, bool with_fac) const
     {
         if (k < 0 || k >= N) return;
-        if (lane < NX) prefetch_l1(Wv + (size_t)k * WT + lane * 16);
-        else if (with_fac && lane < NX + 6) prefetch_l1(reinterpret_cast<const char*>(facv + (size_t)k * FAC) + (lane - NX) * 128);
+        if (!RING && lane < NX) prefetch_l1(Wv + (size_t)k * WT + lane * WR);
+        else if (with_fac && lane >= NX && lane < NX + 6) prefetch_l1(reinterpret_cast<const char*>(facv + (size_t)k * FAC) + (lane - NX) * 128);
     }
 
     // Backward Riccati sweep with factorisation.  Gradient: rt (inputs), q column (states), b column (offset).
@@ -313,12 +402,13 @@ struct WarpCtx {
         }
         __syncwarp();
         const int r0 = 7 * h, o0 = 7 - r0, cb = 8 * h;
+        sweep_begin(N - 1, -1);
         for (int k = N - 1; k >= 0; --k) {
-            const real* tile = Wv + (size_t)k * WT;
+            const real* tile = tile_at(N - 1 - k, k);
             real w[NX];
-            load_col(k, w);
+            load_col(tile, w);
             prefetch_stage(k - 1, false);
-            const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
+            const real qj = sidx >= 0 ? tld(tile + sidx * WR + 15) : real(0);
             // y = P w: rows r0..r0+6 here, rows o0..o0+6 from the partner lane (row 13 is the zero padding row)
             real ym[7], yo[7];
 #pragma unroll
@@ -347,27 +437,28 @@ struct WarpCtx {
             for (int ii = 0; ii < 8; ++ii) m[ii] = 0;
 #pragma unroll
             for (int kk = 0; kk < 7; ++kk) {
-                const real* tr = tile + (r0 + kk < NX ? r0 + kk : NX - 1) * 16 + cb;   // y is 0 on the padding row
+                const real* tr = tile + (r0 + kk < NX ? r0 + kk : NX - 1) * WR + cb;   // y is 0 on the padding row
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
                     real t0, t1;
-                    ldg2(tr + c, t0, t1);
+                    tld2(tr + c, t0, t1);
                     m[c] += t0 * ym[kk]; m[c + 1] += t1 * ym[kk];
                 }
             }
 #pragma unroll
             for (int kk = 0; kk < 7; ++kk) {
-                const real* tr = tile + (o0 + kk < NX ? o0 + kk : NX - 1) * 16 + cb;
+                const real* tr = tile + (o0 + kk < NX ? o0 + kk : NX - 1) * WR + cb;
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
                     real t0, t1;
-                    ldg2(tr + c, t0, t1);
+                    tld2(tr + c, t0, t1);
                     m[c] += t0 * yo[kk]; m[c + 1] += t1 * yo[kk];
                 }
             }
             // cost diagonal of this column (added where the diagonal entry is consumed)
             const real dg = j < 4 ? a.Rd[j] + (FIXED ? real(0) : dR[k * 4 + j]) : (j < 14 ? a.Qd[j - 1] : real(0));
-            __syncwarp();                          // hv visible; every read of the old P is done
+            __syncwarp();                          // hv visible; every read of the old P and of the tile is done
+            tile_done(N - 1 - k, k - RING);
             real g = 0;
 #pragma unroll
             for (int c = 0; c < 12; c += 2) {
@@ -496,9 +587,10 @@ struct WarpCtx {
     {
         if (lane < 16) pv[lane] = 0;
         __syncwarp();
+        sweep_begin(N - 1, -1);
         for (int k = N - 1; k >= 0; --k) {
             real w[NX];
-            load_col(k, w);
+            load_col(tile_at(N - 1 - k, k), w);
             prefetch_stage(k - 1, true);
             const real* f = facv + (size_t)k * FAC;
             Chol4<real> L;
@@ -520,6 +612,7 @@ struct WarpCtx {
             L.fsolve(gu, lgc);
             const real pold = j < 3 ? pv[j] : real(0);
             __syncwarp();
+            tile_done(N - 1 - k, k - RING);
             if (h == 0) {
                 if (j >= 4 && j < 14) pv[j - 1] = g - dot4(lx, lgc);
                 else if (j < 3) pv[j] = pold - dot4(lx, lgc);
@@ -537,12 +630,13 @@ struct WarpCtx {
     {
         if (lane < NX) pv[lane] = a.QNd[lane] * (xtr[(size_t)N * NX + lane] + real(xit[(size_t)N * NX + lane] - yref_e[lane]));
         __syncwarp();
+        sweep_begin(N - 1, -1);
         for (int k = N - 1; k >= 0; --k) {
             real w[NX];
-            load_col(k, w);
+            const real* tile = tile_at(N - 1 - k, k);
+            load_col(tile, w);
             prefetch_stage(k - 1, false);
-            const real* tile = Wv + (size_t)k * WT;
-            const real qj = sidx >= 0 ? __ldg(tile + sidx * 16 + 15) : real(0);
+            const real qj = sidx >= 0 ? tld(tile + sidx * WR + 15) : real(0);
             real g = 0;
 #pragma unroll
             for (int c = 0; c < 12; c += 2) {
@@ -554,6 +648,7 @@ struct WarpCtx {
             const real xk = sidx >= 0 ? xtr[k * NX + sidx] : real(0);
             const real pold = j < 3 ? pv[j] : real(0);
             __syncwarp();
+            tile_done(N - 1 - k, k - RING);
             if (h == 0) {
                 if (j < 4) grad[k * 4 + j] = g + a.Rd[j] * usol[k * 4 + j] + rdel[k * 4 + j];
                 if (j >= 4 && j < 14) pv[j - 1] = g + a.Qd[j - 1] * xk + qj;
@@ -568,9 +663,13 @@ struct WarpCtx {
     // Returns true when the active set is self-consistent: usol then holds the exact minimiser of the box-QP.
     // may_bail: give up early when the change count stops contracting (warm start only: the IPM is the fall-back there;
     // after the IPM the rounds run to max_rounds, because giving up means an IPM-accurate instead of an exact answer)
-    __device__ bool refine_rounds(real lb, real ub, int max_rounds, int& rounds, bool may_bail)
+    // mark_round / mark_counter (screening): an OCP still unsettled after mark_round rounds is counted once
+    __device__ bool refine_rounds(real lb, real ub, int max_rounds, int& rounds, bool may_bail, int bail_round,
+                                  int mark_round = -1, int* mark_counter = nullptr)
     {
         int prev_changed = 1 << 30;
+        ActiveSetHistory hist;
+        hist.init(hist_store);
         for (int round = 0; round < max_rounds; ++round) {
             int pinned = 0;
             for (int e = lane; e < E; e += 32) {
@@ -586,16 +685,22 @@ struct WarpCtx {
             __syncwarp();
             ++rounds;
             int changed = 0;
+            unsigned long long fp = 0;
             for (int e = lane; e < E; e += 32) {
                 const real f = fx[e], un = ubar[e] + usol[e], gr = grad[e];
                 if (f == real(1)) { if (gr < -a.refine_gtol) { fx[e] = 0; ++changed; } }
                 else if (f == real(2)) { if (gr > a.refine_gtol) { fx[e] = 0; ++changed; } }
                 else if (un < lb) { fx[e] = 1; ++changed; }
                 else if (un > ub) { fx[e] = 2; ++changed; }
+                fp += active_set_term(e, fx[e]);
             }
             changed = warp_sum(changed);
+            fp = warp_sum(fp);
             if (!changed) return true;
-            if (may_bail && round >= a.bail_round && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
+            const bool cycling = hist.seen_then_push(fp, lane);   // the deterministic iteration met this active set before: it cycles
+            if ((round + 1 == mark_round || (cycling && round + 1 < mark_round)) && mark_counter && lane == 0) atomicAdd(mark_counter, 1);
+            if (cycling) return false;
+            if (may_bail && round >= bail_round && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
             if (may_bail && round >= 1 && changed > a.bail_changed) return false;
             prev_changed = changed;
         }
@@ -624,11 +729,12 @@ struct WarpCtx {
         }
         __syncwarp();
         const int irow = j < NX ? j : NX - 1;
+        sweep_begin(0, 1);
         for (int k = 0; k < N; ++k) {
-            const real* tr = Wv + (size_t)k * WT + irow * 16 + h * 8;
+            const real* tr = tile_at(k, k) + irow * WR + h * 8;
             real wr[8];
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) ldg2(tr + c, wr[c], wr[c + 1]);
+            for (int c = 0; c < 8; c += 2) tld2(tr + c, wr[c], wr[c + 1]);
             prefetch_stage(k + 1, MODE != 2);
             real u[4];
             if (MODE != 2) {
@@ -650,7 +756,8 @@ struct WarpCtx {
             } else {
                 ld2(usol + k * 4, u[0], u[1]); ld2(usol + k * 4 + 2, u[2], u[3]);
             }
-            __syncwarp();                       // everyone has read the old state
+            __syncwarp();                       // everyone has read the old state (and its part of the tile)
+            tile_done(k, k + RING);
             if (lane < 4) {
                 const real ul = sel4(u, lane);
                 wv[lane] = ul;
@@ -722,6 +829,14 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         c.tl = v + 11 * E; c.tu = v + 12 * E; c.xtr = v + 13 * E;
     }
     c.fx = c.cl; c.fv = c.cu; c.grad = c.ua;
+    c.hist_store = sm + a.ring_off;                      // 48 bytes, then the ring (offsets stay 16-byte aligned)
+    c.ring = sm + a.ring_off + HIST_REALS<real>();
+    c.rbar = reinterpret_cast<unsigned long long*>(c.ring + WarpCtx<real>::RING * WT);
+    c.rphase = 0;
+    if (WarpCtx<real>::RING) {
+        if (lane == 0) for (int s_ = 0; s_ < WarpCtx<real>::RING; ++s_) mbar_init(c.rbar + s_, 1);
+        __syncwarp();
+    }
     c.Wv = a.W + (size_t)ocp * N * WT;
     c.facv = a.fac + (size_t)ocp * N * FAC;
     c.x0 = a.x0 + (size_t)ocp * NX;
@@ -742,21 +857,33 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
 
     int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
     bool exact = false;
+    // screening mode: an OCP whose previous solve needed a long interior-point run (a vehicle far off its reference, most
+    // inputs saturated) will need it again.  It skips the rounds and enters the hard list at once, i.e. near its head: the
+    // dense launch starts its longest items first.
+    const bool long_ipm_last_time = a.hard_count && a.skip_screen_iters > 0 && a.iters[ocp] >= a.skip_screen_iters;
     // ---- 1. warm start: the active set of the previous solve is usually still right (RTI does not shift the horizon)
-    if (a.warm_rounds > 0) {
+    if (a.warm_rounds > 0 && !long_ipm_last_time) {
         int known = 1;
         for (int e = lane; e < E; e += 32) { const unsigned char f = act[e]; if (f > 2) known = 0; c.fx[e] = real(f <= 2 ? f : 0); }
         known = -warp_max(-known);
-        if (known && c.refine_rounds(lb, ub, a.warm_rounds, rounds, true)) { exact = true; status = QMPC_STATUS_OK_; }
-    }
+        // busy step (the previous step left many OCPs unsettled, the dense launch would need several waves): keep the
+        // contracting ones here for more rounds - a Riccati round costs a quarter of the dense kernel's condensing
+        const bool busy = a.unsettled_prev && a.warm_rounds_busy > a.warm_rounds && *a.unsettled_prev > a.busy_threshold;
+        if (known && c.refine_rounds(lb, ub, busy ? a.warm_rounds_busy : a.warm_rounds, rounds, true,
+                                     busy ? a.bail_round_busy : a.bail_round, a.warm_rounds, a.unsettled_cur)) {
+            exact = true; status = QMPC_STATUS_OK_;
+        }
+        if (!known && a.unsettled_cur && lane == 0) atomicAdd(a.unsettled_cur, 1);
+    } else if (long_ipm_last_time && a.unsettled_cur && lane == 0) atomicAdd(a.unsettled_cur, 1);
     if (!exact && a.hard_count) {
         // screening mode: hand the OCP to the dense kernel together with the active-set guess the rounds ended on
-        if (a.warm_rounds > 0) {
+        if (a.warm_rounds > 0 && !long_ipm_last_time) {
             bool was_known = true;
             for (int e = lane; e < E; e += 32) was_known = was_known && act[e] <= 2;
             was_known = warp_max(int(!was_known)) == 0;
             if (was_known) for (int e = lane; e < E; e += 32) act[e] = c.fx[e] == real(1) ? 1 : (c.fx[e] == real(2) ? 2 : 0);
         }
+        if (long_ipm_last_time) for (int e = lane; e < E; e += 32) act[e] = 255;    // the dense kernel starts from its IPM
         if (lane == 0) { a.rounds[ocp] = rounds; a.hard_list[atomicAdd(a.hard_count, 1)] = ocp; }
         return;
     }
@@ -794,7 +921,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
                 if (refine) {
                     for (int e = lane; e < E; e += 32)
                         c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
-                    if (c.refine_rounds(lb, ub, a.max_refine, rounds, a.post_bail != 0)) { status = QMPC_STATUS_OK_; exact = true; break; }
+                    if (c.refine_rounds(lb, ub, a.max_refine, rounds, a.post_bail != 0, a.bail_round)) { status = QMPC_STATUS_OK_; exact = true; break; }
                     // inconsistent active set: one more attempt from a 100x sharper IPM point, then the IPM alone to mu_tol
                     if (++attempts < 2) target *= real(1e-2);
                     else { refine = false; target = a.mu_tol; }

@@ -23,20 +23,29 @@ struct DenseArgs {
     IpmArgs<real> b;
     const int* hard_list;           // OCP indices to solve, or null = all of 0..B-1
     const int* hard_count;          // device counter written by the screening kernel (read here, no host sync)
+    int* next_item;                 // work queue: CTAs take their first item by index and every further one from this counter
+                                    // (zeroed before the launch; IPM and round counts vary 6x between OCPs), or null = strided
 };
 
-// shared-memory carve-up (reals)
+// shared-memory carve-up (reals).  Condensing works in a region that OVERLAYS Ht/Lt (written when it ends):
+//   tiles[N][13][16]          all stage tiles of the OCP, fetched with one TMA bulk copy (cp.async.bulk + mbarrier)
+//   Gc[2][DN_CH][13][GS]      sqrt(Q)-scaled impulse-response columns of DN_CH stages, double-buffered
+//   evc[2][DN_CH][16]         sqrt(Q)-scaled free response + (iterate - reference) of those stages
 struct DenseLayout {
-    int E, T, GS, Ht, Lt, G, ev, sq, sml, tb, dxs, vec, total;
+    int E, T, GS, Ht, Lt, tiles, Gc, evc, sq, sml, dxs, vec, total;
 };
 constexpr int DN_NVEC = 18;
+constexpr int DN_CH = 3;            // stages per condensing chunk (one CTA barrier per chunk)
 __host__ __device__ inline DenseLayout dense_layout(int N)
 {
     DenseLayout L;
     L.E = 4 * N; L.T = N * (N + 1) / 2; L.GS = L.E + 4;
-    L.Ht = 0; L.Lt = L.T * TS; L.G = 2 * L.T * TS; L.ev = L.G + 13 * L.GS; L.sq = L.ev + 16; L.sml = L.sq + 32;
-    L.tb = L.sml + 64;                   // small: wv(16) xp(16) reduction scratch(16) control words(16)
-    L.dxs = L.tb + 2 * WT;               // two staged stage tiles
+    L.Ht = 0; L.Lt = L.T * TS;
+    L.tiles = 0; L.Gc = N * WT; L.evc = L.Gc + 2 * DN_CH * 13 * L.GS;
+    const int cond = L.evc + 2 * DN_CH * 16, fact = 2 * L.T * TS;
+    L.sq = cond > fact ? cond : fact;
+    L.sml = L.sq + 32;                   // small: wv(16) xp(16) reduction scratch(16) control words(8) mbarrier(8)
+    L.dxs = L.sml + 64;
     L.vec = (L.dxs + 13 * (N + 1) + 1) & ~1;
     L.total = L.vec + DN_NVEC * L.E;
     return L;
@@ -86,7 +95,7 @@ template <typename real>
 struct DenseCtx {
     const IpmArgs<real>& a;
     int tid, lane, N, E, T, GS, ti, tj;
-    real *Ht, *Lt, *G, *ev;
+    real *Ht, *Lt;
     real *f, *ubar, *ucur, *tl, *tu, *ll, *lu, *cl, *cu, *ua, *usol, *rt, *dR, *tv, *itl, *itu, *ill, *ilu, *fx, *fv;
 
     // tv = H x  (thread per row; H symmetric, stored as 4x4 tiles of the lower triangle)
@@ -298,12 +307,16 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
     const int T = lay.T, GS = lay.GS;
     DenseCtx<real> c{a};
     c.tid = tid; c.lane = lane; c.N = N; c.E = E; c.T = T; c.GS = GS;
-    c.Ht = sm + lay.Ht; c.Lt = sm + lay.Lt; c.G = sm + lay.G; c.ev = sm + lay.ev;
+    c.Ht = sm + lay.Ht; c.Lt = sm + lay.Lt;
+    real* tiles = sm + lay.tiles;               // condensing / roll-out: the OCP's stage tiles (overlay Ht/Lt)
+    real* Gc = sm + lay.Gc;
+    real* evc = sm + lay.evc;
     real* sq = sm + lay.sq;                     // sqrt of the stage / terminal state weights
     real* small = sm + lay.sml;                 // wv(16) xp(16) red(16) control words
     real* red = small + 32;
     int* ctl = reinterpret_cast<int*>(small + 48);
-    real* tb = sm + lay.tb;                     // two staged stage tiles (condensing)
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(small + 56);
+    unsigned mphase = 0;                        // parity of the next TMA completion on mbar
     real* dxs = sm + lay.dxs;                   // state increments of the roll-out [(N+1)][13]
     real* v = sm + lay.vec;
     c.f = v; c.ubar = v + E; c.ucur = v + 2 * E; c.tl = v + 3 * E; c.tu = v + 4 * E; c.ll = v + 5 * E; c.lu = v + 6 * E;
@@ -319,9 +332,22 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
     const int count = da.hard_list ? *da.hard_count : a.B;
     const real lb = a.lb, ub = a.ub;
     if (tid < NX) { sq[tid] = sqrt(a.Qd[tid]); sq[16 + tid] = sqrt(a.QNd[tid]); }
+    if (tid == 0) mbar_init(mbar, 1);
+    const unsigned tile_bytes = (unsigned)(N * WT * sizeof(real));
+    // condensing roles: thread t < T accumulates tile t of H; thread DN_THREADS-1-c carries impulse-response column c
+    // (c < E) or the free response (c == E) through the stages - the LAST warps, whose tiles join the sum last, so the
+    // propagation of chunk i+1 overlaps the tile accumulation of chunk i
+    const int cidx = DN_THREADS - 1 - tid;
+    const bool colthr = cidx <= E;
+    const int nch = (N + DN_CH - 1) / DN_CH;
     enum { T_FIXED, T_ADJ, T_PRED, T_GRAD, T_DONE };
+    __syncthreads();
 
-    for (int item = blockIdx.x; item < count; item += gridDim.x) {
+    int item = blockIdx.x, qslot = 2;
+    while (item < count) {
+        // next item: fetched now, read after this item's last barrier (two alternating slots: the next write happens while
+        // slower threads may still be reading the previous one)
+        if (tid == 0) ctl[qslot] = da.next_item ? (int)gridDim.x + atomicAdd(da.next_item, 1) : item + (int)gridDim.x;
         const int ocp = da.hard_list ? da.hard_list[item] : item;
         if (a.timeline && tid == 0) a.timeline[2 * ocp] = global_ns();
         DPROF_DECL;
@@ -333,19 +359,19 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
         double* uit = a.uit + (size_t)ocp * N * NU;
         unsigned char* actset = a.act + (size_t)ocp * E;
 
-        // ---- condensing: thread c < E carries impulse-response column c, thread E the free response; thread t < T
-        //      accumulates tile t of H = Rbar + sum_k G_k' Q_k G_k from the sqrt(Q)-scaled columns in shared memory
-        if (tid < WT) tb[tid] = __ldg(Wv + tid);
-        real w1 = 0, w2 = 0;                    // stage tiles k+1 and k+2, two stages of latency cover
-        if (tid < WT && 1 < N) w1 = __ldg(Wv + (size_t)WT + tid);
-        if (tid < WT && 2 < N) w2 = __ldg(Wv + (size_t)2 * WT + tid);
+        // ---- condensing: H = Rbar + sum_k G_k' Q_k G_k, f = Rbar (ubar - uref) + sum_k G_k' Q_k (free response + iterate - ref)
+        if (tid == 0) {                          // every generic access to the overlay region ended at the last barrier
+            fence_proxy_async();
+            mbar_expect(mbar, tile_bytes);
+            bulk_g2s(tiles, Wv, tile_bytes, mbar);
+        }
         for (int idx = NX + tid; idx < (N + 1) * NX; idx += DN_THREADS) {     // iterate minus reference, stages 1..N
             const int k = idx / NX, r = idx - k * NX;
             dxs[idx] = real(xit[idx] - (k < N ? yref[(size_t)k * NY + r] : yref_e[r]));
         }
         real g[NX];
 #pragma unroll
-        for (int r = 0; r < NX; ++r) g[r] = tid == E ? real(x0[r] - xit[r]) : real(0);
+        for (int r = 0; r < NX; ++r) g[r] = cidx == E ? real(x0[r] - xit[r]) : real(0);
         if (tid < E) {
             const real ub_ = real(uit[tid]);
             c.ubar[tid] = ub_;
@@ -355,74 +381,87 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
 #pragma unroll
         for (int t = 0; t < 16; ++t) acc[t] = 0;
         real fc = 0;
-        __syncthreads();
-        for (int k = 0; k < N; ++k) {
-            const real* tile = tb + (k & 1) * WT;
-            const bool colact = (tid < E && (tid >> 2) <= k) || tid == E;
-            const real* sqk = sq + ((k + 1 < N) ? 0 : 16);
-            if (colact) {
-                if (tid < E && (tid >> 2) == k) {
+        // one chunk of the column propagation: stages ch*DN_CH ..., results into buffer ch & 1
+        auto propagate = [&](int ch) {
+            real* Gb = Gc + (ch & 1) * (DN_CH * 13 * GS);
+            real* eb = evc + (ch & 1) * (DN_CH * 16);
+            for (int kk = 0; kk < DN_CH; ++kk) {
+                const int k = ch * DN_CH + kk;
+                if (k >= N) break;
+                const int blk = cidx >> 2;               // stage at which input column cidx enters (E >> 2 == N: never)
+                if (cidx < E && blk > k) continue;
+                const real* tile = tiles + k * WT;
+                const real* sqk = sq + ((k + 1 < N) ? 0 : 16);
+                if (cidx < E && blk == k) {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) g[r] = tile[r * 16 + (tid & 3)];
+                    for (int r = 0; r < NX; ++r) g[r] = tile[r * WR + (cidx & 3)];
                 } else {
                     real gn[NX];
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
                         real s0 = r < 3 ? g[r] : real(0), s1 = 0;
 #pragma unroll
-                        for (int s = 0; s < 10; s += 2) {
+                        for (int s_ = 0; s_ < 10; s_ += 2) {
                             real t0, t1;
-                            ld2(tile + r * 16 + 4 + s, t0, t1);
-                            s0 = fma(t0, g[3 + s], s0); s1 = fma(t1, g[4 + s], s1);
+                            ld2(tile + r * WR + 4 + s_, t0, t1);
+                            s0 = fma(t0, g[3 + s_], s0); s1 = fma(t1, g[4 + s_], s1);
                         }
                         gn[r] = s0 + s1;
                     }
-                    if (tid == E) {
+                    if (cidx == E) {
 #pragma unroll
-                        for (int r = 0; r < NX; ++r) gn[r] += tile[r * 16 + 14];
+                        for (int r = 0; r < NX; ++r) gn[r] += tile[r * WR + 14];
                     }
 #pragma unroll
                     for (int r = 0; r < NX; ++r) g[r] = gn[r];
                 }
-            }
-            DPROF(7);
-            __syncthreads();                    // the tile accumulation of the previous stage has read G
-            DPROF(8);
-            if (colact) {
-                if (tid < E) {
+                if (cidx < E) {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) c.G[r * GS + tid] = sqk[r] * g[r];
+                    for (int r = 0; r < NX; ++r) Gb[(kk * 13 + r) * GS + cidx] = sqk[r] * g[r];
                 } else {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) c.ev[r] = sqk[r] * (g[r] + dxs[(k + 1) * NX + r]);
+                    for (int r = 0; r < NX; ++r) eb[kk * 16 + r] = sqk[r] * (g[r] + dxs[(k + 1) * NX + r]);
                 }
             }
-            if (tid < WT) {
-                if (k + 1 < N) tb[((k + 1) & 1) * WT + tid] = w1;
-                w1 = w2;
-                if (k + 3 < N) w2 = __ldg(Wv + (size_t)(k + 3) * WT + tid);
-            }
-            DPROF(9);
-            __syncthreads();
-            DPROF(10);
-            if (tid < T && ti <= k) {           // H tile += (sqrt(Q) G_i)' (sqrt(Q) G_j)
+        };
+        __syncthreads();                        // dxs is complete (the free-response thread reads it)
+        bulk_wait_block(mbar, mphase); mphase ^= 1;
+        if (colthr) propagate(0);
+        __syncthreads();
+        for (int ch = 0; ch < nch; ++ch) {
+            if (colthr && ch + 1 < nch) propagate(ch + 1);
+            const real* Gb = Gc + (ch & 1) * (DN_CH * 13 * GS);
+            const real* eb = evc + (ch & 1) * (DN_CH * 16);
+            if (tid < T) {                      // H tile += (sqrt(Q) G_i)' (sqrt(Q) G_j) over the stages of the chunk
+                for (int kk = 0; kk < DN_CH; ++kk) {
+                    const int k = ch * DN_CH + kk;
+                    if (k >= N) break;
+                    if (ti > k) continue;
+                    const real* Gk = Gb + kk * 13 * GS;
 #pragma unroll
-                for (int r = 0; r < NX; ++r) {
-                    real gi[4], gj[4];
-                    ld2(c.G + r * GS + 4 * ti, gi[0], gi[1]); ld2(c.G + r * GS + 4 * ti + 2, gi[2], gi[3]);
-                    ld2(c.G + r * GS + 4 * tj, gj[0], gj[1]); ld2(c.G + r * GS + 4 * tj + 2, gj[2], gj[3]);
+                    for (int r = 0; r < NX; ++r) {
+                        real gi[4], gj[4];
+                        ld2(Gk + r * GS + 4 * ti, gi[0], gi[1]); ld2(Gk + r * GS + 4 * ti + 2, gi[2], gi[3]);
+                        ld2(Gk + r * GS + 4 * tj, gj[0], gj[1]); ld2(Gk + r * GS + 4 * tj + 2, gj[2], gj[3]);
 #pragma unroll
-                    for (int p = 0; p < 4; ++p)
+                        for (int p = 0; p < 4; ++p)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[p * 4 + q] = fma(gi[p], gj[q], acc[p * 4 + q]);
+                            for (int q = 0; q < 4; ++q) acc[p * 4 + q] = fma(gi[p], gj[q], acc[p * 4 + q]);
+                    }
                 }
             }
-            if (tid < E && (tid >> 2) <= k) {
+            if (tid < E) {                      // gradient entry of input tid
+                for (int kk = 0; kk < DN_CH; ++kk) {
+                    const int k = ch * DN_CH + kk;
+                    if (k >= N) break;
+                    if ((tid >> 2) > k) continue;
 #pragma unroll
-                for (int r = 0; r < NX; ++r) fc = fma(sqk[r] * g[r], c.ev[r], fc);
+                    for (int r = 0; r < NX; ++r) fc = fma(Gb[(kk * 13 + r) * GS + tid], eb[kk * 16 + r], fc);
+                }
             }
-            DPROF(11);
+            __syncthreads();                    // buffer (ch+1)&1 is complete; nobody reads buffer ch&1 any more
         }
+        // every read of the overlay region ended at the barrier above: Ht may be written
         if (tid < T) {
             if (ti == tj) {
 #pragma unroll
@@ -438,7 +477,9 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
         // round here), the IPM from the box centre if there is no guess or the rounds do not settle.
         int it = 0, rounds = 0, status = QMPC_STATUS_MAXITER_;
         bool exact = false, refine = a.max_refine > 0, ipm_started = false;
-        int rounds_left = 0, prev_changed = 1 << 30, round_no = 0, attempts = 0;
+        int rounds_left = 0, prev_changed = 1 << 30, best_changed = 1 << 28, round_no = 0, attempts = 0;
+        ActiveSetHistory hist;              // warp 0: fingerprints of the active sets of this attempt (cycle detection)
+        hist.init(small + 57);              // 6 x 8 bytes of the scratch block
         if (warp == 0) {
             int known = a.dense_warm_rounds > 0 && da.hard_list != nullptr;
             DN_FOR_E(e) { const unsigned char fl = actset[e]; if (fl > 2) known = 0; c.fx[e] = real(fl <= 2 ? fl : 0); }
@@ -505,6 +546,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                 } else if (trip == T_ADJ) {
                     ++rounds;
                     int changed = 0;
+                    unsigned long long fp = 0;
                     DN_FOR_E(e) {
                         const real fxe = c.fx[e], un = c.ubar[e] + c.usol[e], gr = c.tv[e] + c.f[e];
                         real fn = fxe;
@@ -514,11 +556,28 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                         else if (un > ub) fn = 2;
                         if (fn != fxe) { ++changed; c.fx[e] = fn; }
                         c.fv[e] = fn == real(1) ? lb - c.ubar[e] : (fn == real(2) ? ub - c.ubar[e] : real(0));
+                        fp += active_set_term(e, fn);
                     }
                     changed = warp_sum(changed);
+                    fp = warp_sum(fp);
+                    // the primal-dual active-set iteration is a deterministic map of the active set: meeting a set again
+                    // means it cycles (period 3-4 in practice) and will never settle from this start
+                    const bool cycling = hist.seen_then_push(fp, lane) && changed;
                     ++round_no;
+#ifdef QMPC_EMU_TRACE
+                    if (lane == 0) {
+                        int np_ = 0; real gmin = 1e30;
+                        for (int e = 0; e < E; ++e) if (c.fx[e] != real(0)) ++np_;
+                        printf("  [trace ocp %d] round %d (ipm_started %d it %d): changed %d pinned %d cycling %d\n", ocp, round_no, (int)ipm_started, it, changed, np_, (int)cycling);
+                    }
+#endif
                     if (!changed) { exact = true; status = QMPC_STATUS_OK_; next = T_DONE; }
-                    else if (--rounds_left > 0 && !((!ipm_started || a.post_bail) && round_no >= 3 && changed >= prev_changed)) { prev_changed = changed; next = T_FIXED; }   // after the IPM (fp64) the rounds never give up early
+                    else if (--rounds_left > 0 && !cycling && !(ipm_started && round_no >= 2 && changed > 2 * best_changed + 2) &&
+                             !((!ipm_started || a.post_bail) && round_no >= 3 && changed >= prev_changed)) {
+                        // after the IPM (fp64) the rounds only give up on a proven cycle or when the change count runs away
+                        // from its best value (a diverging iteration wanders for all its rounds; the sharper restart settles)
+                        prev_changed = changed; best_changed = changed < best_changed ? changed : best_changed; next = T_FIXED;
+                    }
                     else if (!ipm_started) {     // the warm rounds did not settle: IPM from the box centre
                         DN_FOR_E(e) c.usol[e] = real(0.5) * (lb + ub) - c.ubar[e];
                         next = T_GRAD;
@@ -582,6 +641,9 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                         }
                         resfac *= real(1) - fmin(ap, ad);
                         ++it;
+#ifdef QMPC_EMU_TRACE
+                        if (lane == 0) printf("  [trace ocp %d] ipm it %d: mu %.3e sigma %.3e ap %.4f ad %.4f resfac %.3e cpass %d\n", ocp, it, (double)mu, (double)sigma, (double)ap, (double)ad, (double)resfac, cpass);
+#endif
                         break;
                     }
                     next = T_PRED;
@@ -599,7 +661,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                                 c.fx[e] = fn;
                                 c.fv[e] = fn == real(1) ? lb - c.ubar[e] : (fn == real(2) ? ub - c.ubar[e] : real(0));
                             }
-                            next = T_FIXED; rounds_left = a.max_refine; prev_changed = 1 << 30; round_no = 0;
+                            next = T_FIXED; rounds_left = a.max_refine; prev_changed = 1 << 30; best_changed = 1 << 28; round_no = 0; hist.clear();
                         } else { status = QMPC_STATUS_OK_; next = T_DONE; }
                     } else if (it >= iter_limit(a, ocp)) next = T_DONE;
                 }
@@ -609,8 +671,13 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
             }
             __syncthreads();
         }
-        // ---- result: new iterate, states re-rolled through the linearised dynamics
-        for (int idx = tid; idx < N * NX; idx += DN_THREADS) prefetch_l1(Wv + (size_t)idx * 16);
+        // ---- result: new iterate, states re-rolled through the linearised dynamics.  Ht/Lt are dead: the stage tiles
+        //      come back into the overlay region with one more TMA bulk copy while warp 0 finalises the inputs.
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect(mbar, tile_bytes);
+            bulk_g2s(tiles, Wv, tile_bytes, mbar);
+        }
         if (warp == 0) {
             real chk = 0;
             DN_FOR_E(e) { const real un = exact ? c.usol[e] : c.ucur[e]; chk += un - un; }
@@ -639,37 +706,29 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     uit[e] = double(un);
                 }
                 if (lane < 4) a.u0[(size_t)ocp * 4 + lane] = double(c.ucur[lane]);
-                __syncwarp();
-                // dx_{k+1} = A dx_k + B du_k + b_k, lane j < 13 = row j of the stage tile
-                real* wv = small;
-                real* xp = small + 16;
+            }
+            // dx_{k+1} = A dx_k + B du_k + b_k: lane j < 13 owns row j of the stage tile and walks its 16 columns starting
+            // at column j (rows are 128 B apart: the rotation keeps the lanes on different banks)
+            real* wv = small;                   // [du(4), dx_3..12(10), 1, 0]
+            real* xp = small + 16;              // dx_0..2 (the position columns of A are unit vectors)
+            if (lane < NX) {
+                const real d0 = real(x0[lane] - xit[lane]);
+                if (lane < 3) xp[lane] = d0; else wv[lane + 1] = d0;
+            } else if (lane == 14) wv[14] = 1;
+            else if (lane == 15) wv[15] = 0;
+            bulk_wait_warp(mbar, mphase);       // the tiles have landed (waited for on the NaN path too: the barrier is reused)
+            if (good) {
                 const int j = lane < NX ? lane : NX - 1;
-                if (lane < NX) {
-                    const real d0 = real(x0[lane] - xit[lane]);
-                    if (lane < 3) xp[lane] = d0; else wv[lane + 1] = d0;
-                } else if (lane == 14) wv[14] = 1;
-                else if (lane == 15) wv[15] = 0;
-                __syncwarp();
-                real wn[16];
-#pragma unroll
-                for (int q = 0; q < 16; q += 2) ldg2(Wv + j * 16 + q, wn[q], wn[q + 1]);
                 for (int k = 0; k < N; ++k) {
-                    real wr[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) wr[q] = wn[q];
-                    if (k + 1 < N) {
-                        const real* tr = Wv + (size_t)(k + 1) * WT + j * 16;
-#pragma unroll
-                        for (int q = 0; q < 16; q += 2) ldg2(tr + q, wn[q], wn[q + 1]);
-                    }
                     if (lane < 4) wv[lane] = c.usol[k * 4 + lane];
                     __syncwarp();
+                    const real* tr = tiles + k * WT + j * WR;
                     real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
                     for (int q = 0; q < 16; q += 4) {
-                        real v0, v1, v2, v3;
-                        ld2(wv + q, v0, v1); ld2(wv + q + 2, v2, v3);
-                        s0 = fma(wr[q], v0, s0); s1 = fma(wr[q + 1], v1, s1); s2 = fma(wr[q + 2], v2, s2); s3 = fma(wr[q + 3], v3, s3);
+                        const int c0 = (q + j) & 15, c1 = (q + 1 + j) & 15, c2 = (q + 2 + j) & 15, c3 = (q + 3 + j) & 15;
+                        s0 = fma(tr[c0], wv[c0], s0); s1 = fma(tr[c1], wv[c1], s1);
+                        s2 = fma(tr[c2], wv[c2], s2); s3 = fma(tr[c3], wv[c3], s3);
                     }
                     real accx = (s0 + s1) + (s2 + s3);
                     if (lane < 3) accx += xp[lane];
@@ -682,6 +741,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                 }
             }
         }
+        mphase ^= 1;
         __syncthreads();
         DPROF(4);
         if (ctl[1]) {       // new states and objective, all threads
@@ -710,10 +770,12 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
         if (a.timeline && tid == 0) a.timeline[2 * ocp + 1] = global_ns();
 #ifdef QMPC_DENSE_PROF
         if (tid == 0 && item < 3)
-            printf("dense ocp %d it %d rounds %d | cycles: condense %lld | matvec %lld (%d) | factor %lld (%d) | solves %lld (%d) | logic %lld | rollout %lld | loop-top %lld | total %lld || condense: col %lld sync1 %lld store %lld sync2 %lld tile %lld\n",
-                   ocp, it, rounds, pf_acc[0], pf_acc[1], pf_n[1], pf_acc[2], pf_n[2], pf_acc[3], pf_n[3], pf_acc[6], pf_acc[4], pf_acc[5], clock64() - pf_t0, pf_acc[7], pf_acc[8], pf_acc[9], pf_acc[10], pf_acc[11]);
+            printf("dense ocp %d it %d rounds %d | cycles: condense %lld | matvec %lld (%d) | factor %lld (%d) | solves %lld (%d) | logic %lld | rollout %lld | loop-top %lld | total %lld\n",
+                   ocp, it, rounds, pf_acc[0], pf_acc[1], pf_n[1], pf_acc[2], pf_n[2], pf_acc[3], pf_n[3], pf_acc[6], pf_acc[4], pf_acc[5], clock64() - pf_t0);
 #endif
         __syncthreads();
+        item = ctl[qslot];
+        qslot ^= 1;
     }
 }
 

@@ -65,12 +65,18 @@ class ClosedLoop:
     """
 
     def __init__(self, quad, quad_opt, traj, x_init, simulation_dt=5e-3, shared_swarm=None):
+        """traj: sampled references [B,K,13] (chunked on the GPU), or a trajectory.DeviceReference (generated on the GPU)"""
         self.quad, self.opt = quad, quad_opt
         self.shared_swarm = shared_swarm          # swarm.SharedSwarmRGP: one RGP for all vehicles / ranks (config 3)
         self.B, self.N, self.dev = quad_opt.batch, quad_opt.n_nodes, quad_opt.device
-        self.traj = traj.to(self.dev, torch.float64).contiguous()
-        assert self.traj.shape[0] == self.B and self.traj.shape[2] == 13
-        self.K = self.traj.shape[1]
+        self.refgen = None
+        if torch.is_tensor(traj):
+            self.traj = traj.to(self.dev, torch.float64).contiguous()
+            assert self.traj.shape[0] == self.B and self.traj.shape[2] == 13
+            self.K = self.traj.shape[1]
+        else:
+            self.refgen, self.traj, self.K = traj, None, traj.K
+            assert traj.B == self.B
         self.x = x_init.to(self.dev, torch.float64).contiguous().clone()
         self.x_pred_prev = torch.zeros_like(self.x)
         self.chunk = torch.empty((self.B, self.N, 13), dtype=torch.float64, device=self.dev)
@@ -83,15 +89,23 @@ class ClosedLoop:
     def control(self, x_now, i):
         """controller half of the step for an externally supplied state (end-to-end path: host buffers in/out)"""
         lib, s = _capi.lib(), _capi.stream_ptr()
-        _capi.check(lib.qmpc_reference_chunk(self.B, self.K, _capi.ptr(self.traj), int(i), self.N, 1, _capi.ptr(self.chunk), s))
-        self.opt.step(x_now, self.chunk, self.x_pred_prev, first_step=(i == 0), u0_out=self.u0)
-        if self.shared_swarm is not None:         # accumulate on the GPU -> all-reduce -> identical posterior on every rank
-            self.shared_swarm.update()
+        if self.refgen is not None:
+            self.refgen.chunk(i, self.N, self.chunk)
+        else:
+            _capi.check(lib.qmpc_reference_chunk(self.B, self.K, _capi.ptr(self.traj), int(i), self.N, 1, _capi.ptr(self.chunk), s))
+        if self.shared_swarm is not None:
+            # shared model: residual -> accumulate -> all-reduce -> apply on a side stream, overlapped with this step's solve
+            # (identical posterior on every rank; the solve of step t uses the model pushed after step t-1)
+            self.shared_swarm.begin(x_now, self.x_pred_prev, first_step=(i == 0))
+            self.opt.step(x_now, self.chunk, self.x_pred_prev, first_step=(i == 0), u0_out=self.u0, rgp=False)
+            self.shared_swarm.end()
+        else:
+            self.opt.step(x_now, self.chunk, self.x_pred_prev, first_step=(i == 0), u0_out=self.u0)
         return self.u0
 
     def step(self):
         lib, s = _capi.lib(), _capi.stream_ptr()
-        if self.shared_swarm is None:        # one C call: chunk -> solve -> u0 -> prediction -> residual -> RGP -> plant
+        if self.shared_swarm is None and self.refgen is None:   # one C call: chunk -> solve -> u0 -> prediction -> residual -> RGP -> plant
             g = self.opt.gpe._h if self.opt.gpe is not None else C.c_void_p(0)
             _capi.check(lib.qmpc_closed_loop_step(self.opt._h, g, _capi.ptr(self.traj), self.K, int(self.i), _capi.ptr(self.x),
                                                   _capi.ptr(self.x_pred_prev), _capi.ptr(self.chunk), _capi.ptr(self.u0),

@@ -23,7 +23,7 @@ class quad_optimizer:
     def __init__(self, quad, t_horizon=1, n_nodes=100, gpe=None, batch=None, device=None, precision=64,
                  ipm_mu_tol=0.0, ipm_max_iter=50, ipm_mu_switch=0.0, refine_max_rounds=0, warm_start_rounds=0,
                  solver_variant=0, reset_on_fail=0, screen_rounds=0, dense_warm_rounds=0, bail_round=0, bail_changed=0,
-                 final_rollout=0, dense_grid=0):
+                 final_rollout=0, dense_grid=0, screen_rounds_busy=0, screen_busy_pct=0):
         """The arguments after `gpe` have no counterpart in the reference (one vehicle, acados defaults): batch/device/
         precision select the GPU path, the rest is the per-handle solver policy of include/qmpc.h (0 = library default;
         reset_on_fail=-1 keeps whatever a failed solve left, which is what the reference does, quad_opt.py:333)."""
@@ -52,6 +52,7 @@ class quad_optimizer:
         cfg.solver_variant, cfg.reset_on_fail, cfg.screen_rounds = solver_variant, reset_on_fail, screen_rounds
         cfg.dense_warm_rounds, cfg.bail_round, cfg.bail_changed = dense_warm_rounds, bail_round, bail_changed
         cfg.final_rollout, cfg.dense_grid = final_rollout, dense_grid
+        cfg.screen_rounds_busy, cfg.screen_busy_pct = screen_rounds_busy, screen_busy_pct
         cfg.quad[:] = list(quad.quad_vector())
         cfg.w_diag[:] = list(np.diag(self.W))
         cfg.we_diag[:] = list(np.diag(self.W_e))
@@ -161,6 +162,16 @@ class quad_optimizer:
         _capi.check(_capi.lib().qmpc_get_refine_rounds(self._h, _capi.ptr(r), self._s()))
         return r
 
+    def get_active_set(self):
+        """remembered active sets [B, 4N] uint8 (0 free, 1 lower, 2 upper, 255 unknown)"""
+        a = torch.empty((self.batch, 4 * self.n_nodes), dtype=torch.uint8, device=self.device)
+        _capi.check(_capi.lib().qmpc_get_active_set(self._h, _capi.ptr(a), self._s()))
+        return a
+
+    def set_active_set(self, act):
+        a = act.to(self.device, torch.uint8).reshape(self.batch, 4 * self.n_nodes).contiguous()
+        _capi.check(_capi.lib().qmpc_set_active_set(self._h, _capi.ptr(a), self._s()))
+
     def reset_warm_start(self):
         _capi.check(_capi.lib().qmpc_reset_warm_start(self._h, self._s()))
 
@@ -208,9 +219,10 @@ class quad_optimizer:
         return mu_g_t, C_g_t
 
     # ---- fused closed-loop step (execute_trajectory.py:196-277 in one call, all on the GPU) ------------------------------
-    def step(self, x_now, x_ref, x_pred_prev, first_step, u0_out=None):
+    def step(self, x_now, x_ref, x_pred_prev, first_step, u0_out=None, rgp=True):
         """reference chunk -> solve -> u0 -> nominal prediction -> residual -> RGP regress -> alpha for the next solve.
-        x_now [B,13], x_ref [B,N,13], x_pred_prev [B,13] (updated in place), u0_out [B,4] (optional) CUDA tensors."""
-        g = self.gpe._h if self.gpe is not None else C.c_void_p(0)
+        x_now [B,13], x_ref [B,N,13], x_pred_prev [B,13] (updated in place), u0_out [B,4] (optional) CUDA tensors.
+        rgp=False: solve and prediction only (the RGP update of this step is run elsewhere, swarm.SharedSwarmRGP.begin)."""
+        g = self.gpe._h if (self.gpe is not None and rgp) else C.c_void_p(0)
         _capi.check(_capi.lib().qmpc_step(self._h, g, _capi.ptr(x_now), _capi.ptr(x_ref), _capi.ptr(x_pred_prev),
                                           int(bool(first_step)), _capi.ptr(u0_out), self._s()))

@@ -6,7 +6,15 @@ RGP drag model serves every vehicle: each rank reduces the information-form cont
 (qrgp_shared_accumulate), the [3, M*M+M] fp64 block is all-reduced (NCCL over NVLink; gloo in the CPU tests), and every
 rank applies the identical posterior update (qrgp_shared_apply), so no broadcast is needed.
 This is new semantics (the reference never regresses more than one sample per call); it is defined as
-"apply the single-sample RGP.regress for every vehicle with gain and innovation evaluated at the pre-update model"."""
+"apply the single-sample RGP.regress (reference src/gp/RGP.py:303-330) for every vehicle of every rank, one after the
+other".  The gain row J and the prior variance of a sample depend only on its input and on the fixed basis, so this
+sequence of Kalman updates equals ONE information-form update with the summed J'J/r and J'y/r - exact, and independent
+of the order of the vehicles.
+
+Overlap: the residual of control step t needs only x_now and the PREVIOUS step's prediction, both known before the
+solve of step t, and the solve of step t uses the model pushed after step t-1 (the reference pushes the means after its
+solve, quad_opt.py:402-404).  `begin()` therefore runs residual -> accumulate -> all-reduce -> apply on a side stream
+while the main stream linearises and solves; `end()` joins the two and swaps the double-buffered alpha."""
 import ctypes as C
 
 import torch
@@ -38,7 +46,20 @@ class SharedSwarmRGP:
         assert quad_opt.gpe is gpe
         self.gpe, self.opt, self.group = gpe, quad_opt, group
         self.M = gpe.M
-        self.info = torch.zeros((3, self.M * self.M + self.M), dtype=torch.float64, device=gpe.device)
+        dev = gpe.device
+        self.info = torch.zeros((3, self.M * self.M + self.M), dtype=torch.float64, device=dev)
+        # overlapped path: side stream, residual buffers, double-buffered alpha [2][3][M]
+        self.side = torch.cuda.Stream(device=dev)
+        self.xt = torch.zeros((quad_opt.batch, 3), dtype=torch.float64, device=dev)
+        self.yt = torch.zeros((quad_opt.batch, 3), dtype=torch.float64, device=dev)
+        self.alpha_buf = torch.zeros((2, 3, self.M), dtype=torch.float64, device=dev)
+        self.cur = 0
+        self._res_done = torch.cuda.Event()
+        self._done = torch.cuda.Event()
+        self._t0 = self._t1 = None          # optional timing events around the all-reduce (bench)
+        self.time_allreduce = False
+        self.allreduce_ms = []
+        self._pending = False
 
     def accumulate(self, v_body=None, a_drag=None):
         """information-form sums over this rank's vehicles; default inputs = residuals left by quad_optimizer.step"""
@@ -60,6 +81,44 @@ class SharedSwarmRGP:
         _capi.check(_capi.lib().qrgp_shared_apply(self.gpe._h, _capi.ptr(self.info), _capi.stream_ptr()))
 
     def update(self, v_body=None, a_drag=None):
-        """one shared-model update per control step: accumulate -> all-reduce -> apply"""
+        """one shared-model update per control step on the current stream: accumulate -> all-reduce -> apply"""
         self.accumulate(v_body, a_drag)
         self.exchange_and_apply()
+
+    # ---- overlapped update (see module docstring) -------------------------------------------------------------
+    def begin(self, x_now, x_pred_prev, first_step):
+        """queue residual -> accumulate -> all-reduce -> apply of THIS control step on the side stream.  The caller then
+        queues the solve on the current stream with `quad_optimizer.step(..., rgp=False)` and calls end()."""
+        lib = _capi.lib()
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)                       # x_now / x_pred_prev of this step are ready
+        with torch.cuda.stream(self.side):
+            s = _capi.stream_ptr()
+            xp = x_now if first_step else x_pred_prev     # reference: the first residual is taken against the state itself
+            _capi.check(lib.qmpc_compute_a_drag(self.opt.batch, _capi.ptr(x_now), _capi.ptr(xp),
+                                                C.c_double(self.opt.optimization_dt), _capi.ptr(self.xt), _capi.ptr(self.yt), s))
+            self._res_done.record(self.side)
+            _capi.check(lib.qrgp_shared_accumulate(self.gpe._h, self.opt.batch, _capi.ptr(self.xt), _capi.ptr(self.yt),
+                                                   _capi.ptr(self.info), s))
+            if self.time_allreduce:
+                self._t0 = torch.cuda.Event(enable_timing=True); self._t1 = torch.cuda.Event(enable_timing=True)
+                self._t0.record(self.side)
+            allreduce_info(self.info, self.group)
+            if self.time_allreduce:
+                self._t1.record(self.side)
+            _capi.check(lib.qrgp_shared_apply(self.gpe._h, _capi.ptr(self.info), s))
+            nxt = self.alpha_buf[self.cur ^ 1]
+            _capi.check(lib.qrgp_get_alpha(self.gpe._h, _capi.ptr(nxt), s))
+            self._done.record(self.side)
+        main.wait_event(self._res_done)                   # the solve's epilogue overwrites x_pred_prev
+        self._pending = True
+
+    def end(self):
+        """join: later work on the current stream sees the updated model; the next solve reads the new alpha buffer"""
+        assert self._pending
+        torch.cuda.current_stream().wait_event(self._done)
+        self.cur ^= 1
+        _capi.check(_capi.lib().qmpc_bind_alpha(self.opt._h, _capi.ptr(self.alpha_buf[self.cur]), 0))
+        if self.time_allreduce and self._t0 is not None:
+            self.allreduce_ms.append((self._t0, self._t1))
+        self._pending = False

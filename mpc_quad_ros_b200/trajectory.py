@@ -1,7 +1,17 @@
 """Reference trajectories [K,13] (q = (1,0,0,0), r = 0 as in TrajectoryGenerator.load_trajectory,
-reference src/trajectory_generation/TrajectoryGenerator.py:223-244).  Host-side numpy set-up code; the
-per-step chunking runs on the GPU (utils.get_reference_chunk -> qmpc_reference_chunk)."""
+reference src/trajectory_generation/TrajectoryGenerator.py:223-244).
+
+Two ways to feed a closed loop:
+  * sampled on the host once (`*_trajectories`, numpy set-up code) and chunked on the GPU every step
+    (utils.get_reference_chunk -> qmpc_reference_chunk), or
+  * generated on the GPU every step from per-vehicle parameters (`*_params` -> `DeviceReference` ->
+    qmpc_reference_generate): nothing but the vehicle state ever crosses the host/device boundary."""
+import ctypes as C
+
 import numpy as np
+
+REFGEN_NPAR = 32          # include/qmpc.h QMPC_REFGEN_NPAR
+KIND_SINUSOIDS, KIND_LEMNISCATE, KIND_CIRCLE = 0, 1, 2
 
 
 def _to_state(p, v):
@@ -75,3 +85,63 @@ def lemniscate_trajectories(B, K, dt, v_peak=15.0, a=10.0, z0=3.0, seed=1234):
         p[:, :2] -= p[0, :2]
         out[b] = _to_state(p, v)
     return out
+
+
+# ---- per-vehicle generator parameters (layout: include/qmpc.h qmpc_reference_generate) ----------------------------------
+
+def random_smooth_params(B, K, dt, seed=1234, v_max=10.0, z0=3.0, a_max=None):
+    """parameters [B,32] of the `random_smooth_trajectories` of the same arguments (same Philox streams, same scaling)"""
+    t = np.arange(K) * dt
+    par = np.zeros((B, REFGEN_NPAR))
+    for b in range(B):
+        rng = np.random.Generator(np.random.Philox(key=seed + b))
+        amp, f, ph = rng.uniform(1, 5, (3, 3)), rng.uniform(0.05, 0.3, (3, 3)), rng.uniform(0, 2 * np.pi, (3, 3))
+        arg = 2 * np.pi * f[:, :, None] * t[None, None, :] + ph[:, :, None]
+        v = (amp[:, :, None] * 2 * np.pi * f[:, :, None] * np.cos(arg)).sum(1)
+        s = min(1.0, v_max / max(np.linalg.norm(v, axis=0).max(), 1e-9))
+        if a_max is not None:
+            acc = -(amp[:, :, None] * (2 * np.pi * f[:, :, None]) ** 2 * np.sin(arg)).sum(1)
+            s = min(s, a_max / max(np.linalg.norm(acc, axis=0).max(), 1e-9))
+        p0 = (amp * np.sin(ph)).sum(1) * s
+        par[b, 0:9], par[b, 9:18], par[b, 18:27] = amp.ravel(), f.ravel(), ph.ravel()
+        par[b, 27], par[b, 28:31], par[b, 31] = s, p0, z0
+    return par
+
+
+def lemniscate_params(B, v_peak=15.0, a=10.0, z0=3.0, seed=1234, ramp=3.0):
+    """parameters [B,32] of `lemniscate_trajectories`"""
+    w = v_peak / (a * np.sqrt(2.0))
+    par = np.zeros((B, REFGEN_NPAR))
+    for b in range(B):
+        rng = np.random.Generator(np.random.Philox(key=seed + b))
+        ph, yaw = rng.uniform(0, 2 * np.pi), rng.uniform(0, 2 * np.pi)
+        px, py = a * np.sin(ph), a * np.sin(ph) * np.cos(ph)
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        par[b, :8] = [ph, yaw, w, a, z0, c * px - s_ * py, s_ * px + c * py, ramp]
+    return par
+
+
+def circle_params(radius, v_max, t_max=10, dt=0.01, start_point=np.zeros(3), csv_rounding=True, B=1):
+    """parameters [B,32] of `sample_circle_trajectory_accelerating` (the same circle for every vehicle)"""
+    n = len(np.arange(0, t_max, dt))
+    par = np.zeros((B, REFGEN_NPAR))
+    par[:, 0], par[:, 1], par[:, 2], par[:, 3:6], par[:, 6] = radius, v_max, n, start_point, float(bool(csv_rounding))
+    return par
+
+
+class DeviceReference:
+    """reference generator on the GPU: `chunk(idx, N, out)` fills out [B,N,13] with what
+    utils.get_reference_chunk(trajectory, idx, N, skip) would return for the sampled trajectory of K rows"""
+
+    def __init__(self, kind, params, K, dt, device="cuda:0"):
+        import torch
+        self.kind, self.K, self.dt = int(kind), int(K), float(dt)
+        self.params = torch.as_tensor(np.ascontiguousarray(params, dtype=np.float64), device=device).contiguous()
+        assert self.params.shape[1] == REFGEN_NPAR
+        self.B = self.params.shape[0]
+
+    def chunk(self, idx, N, out, skip=1):
+        from . import _capi
+        _capi.check(_capi.lib().qmpc_reference_generate(self.kind, self.B, _capi.ptr(self.params), self.K, int(idx), int(N), int(skip),
+                                                        C.c_double(self.dt), _capi.ptr(out), _capi.stream_ptr()))
+        return out

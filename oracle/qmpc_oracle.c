@@ -405,7 +405,7 @@ static int boxqp_solve(const qp_t *qp, double *xs, double *us, int *iters_out, d
     double *uc = buf + 6 * n, *dla = buf + 7 * n, *dua = buf + 8 * n, *tl = buf + 9 * n, *tu = buf + 10 * n;
     double *xw = buf + 11 * n;
     double lb = qp->lb, ub = qp->ub;
-    /* initial multipliers scaled with the problem: clip(0.01 * mean |dJ/du| at the box centre, 0.1, 100) */
+    /* initial multipliers scaled with the problem: clip(0.02 * mean |dJ/du| at the box centre, 0.1, 1e5) */
     double lam0 = 0.1;
     {
         double *g0 = (double *)malloc(sizeof(double) * n);
@@ -414,7 +414,7 @@ static int boxqp_solve(const qp_t *qp, double *xs, double *us, int *iters_out, d
         double gs = 0;
         for (int i = 0; i < n; ++i) gs += fabs(g0[i]);
         gs /= n;
-        if (gs == gs) lam0 = fmin(fmax(0.01 * gs, 0.1), 100.0);
+        if (gs == gs) lam0 = fmin(fmax(0.02 * gs, 0.1), 1e5);
         free(g0);
     }
     for (int i = 0; i < n; ++i) { u[i] = 0.5 * (lb + ub); tl[i] = u[i] - lb; tu[i] = ub - u[i]; ll[i] = lam0; lu[i] = lam0; }

@@ -42,6 +42,8 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
         } else if (hard_out) *hard_out = B;
         DenseArgs<real> dn;
         dn.b = ia; dn.hard_list = screen ? list.data() : nullptr; dn.hard_count = screen ? cnt.data() : nullptr;
+        int next = 0;
+        dn.next_item = &next;
         if constexpr (sizeof(real) == 8)
             emu::launch(2, DN_THREADS, (size_t)dense_layout(N).total * sizeof(real), [&]() { qmpc_dense_kernel<real>(dn); });
     }

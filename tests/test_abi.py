@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_layout_matches_header():
     from mpc_quad_ros_b200._capi import QmpcConfig
-    # 8 ints + 3 doubles + 20 + 17 + 13 + 2 + 9 doubles + pointer + 8 policy ints
-    assert ctypes.sizeof(QmpcConfig) == 8 * 4 + (3 + 20 + 17 + 13 + 2 + 9) * 8 + 8 + 8 * 4
+    # 8 ints + 3 doubles + 20 + 17 + 13 + 2 + 9 doubles + pointer + 10 policy ints
+    assert ctypes.sizeof(QmpcConfig) == 8 * 4 + (3 + 20 + 17 + 13 + 2 + 9) * 8 + 8 + 10 * 4
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -496,3 +496,144 @@ def test_rgp_predict_cov_and_gain_vs_reference_code(golden, tag):
     assert np.allclose(v2, np.diag(C_p)) and np.array_equal(J2, Jt)
     m3, J3 = r.predict(xs, return_Jt=True)
     assert np.array_equal(m3, mean) and J3.shape == (xs.shape[0], X.shape[0])
+
+
+# ------------------------------------------------------------------------------------------ round 2 additions
+
+def test_device_reference_generators_match_host_sampling():
+    """qmpc_reference_generate against the host-sampled trajectories cut with utils.get_reference_chunk:
+    sinusoid sums (config 2), lemniscate (config 5) and the reference's accelerating circle incl. its '%.6f' rounding
+    (config 1, TrajectoryGenerator.py:41-74), with end padding and skip"""
+    from mpc_quad_ros_b200 import trajectory as T
+    from mpc_quad_ros_b200.utils import utils
+    B, N, dt = 7, 20, 0.05
+    K = 90
+    cases = [
+        (T.KIND_SINUSOIDS, T.random_smooth_params(B, K, dt, seed=77), T.random_smooth_trajectories(B, K, dt, seed=77), 1e-12),
+        (T.KIND_LEMNISCATE, T.lemniscate_params(B, v_peak=20.0, seed=5), T.lemniscate_trajectories(B, K, dt, v_peak=20.0, seed=5), 1e-12),
+    ]
+    circ, ts = T.sample_circle_trajectory_accelerating(10, 10, 30, dt)
+    cases.append((T.KIND_CIRCLE, T.circle_params(10, 10, 30, dt, B=2), np.stack([circ, circ]), 0.0))
+    for kind, par, traj, tol in cases:
+        Bk, Kk = traj.shape[0], traj.shape[1]
+        gen = T.DeviceReference(kind, par, Kk, dt)
+        out = torch.empty((Bk, N, 13), dtype=torch.float64, device="cuda")
+        for idx, skip in ((0, 1), (17, 1), (Kk - N - 1, 1), (Kk - 5, 1), (Kk - 1, 1), (3, 2), (Kk - 25, 2), (Kk - 2, 3)):
+            gen.chunk(idx, N, out, skip=skip)
+            got = out.cpu().numpy()
+            for b in range(Bk):
+                want = utils.get_reference_chunk(traj[b], idx, N, skip)
+                err = np.abs(got[b] - want).max()
+                assert err <= tol, (kind, idx, skip, b, err)
+
+
+def test_closed_loop_with_device_reference_equals_sampled_reference():
+    """ClosedLoop fed by DeviceReference (nothing but the state crosses the boundary) against the same loop fed by the
+    host-sampled trajectory: references agree to 1e-12, so the closed loops stay together"""
+    from mpc_quad_ros_b200 import trajectory as T
+    from mpc_quad_ros_b200.execute_trajectory import ClosedLoop
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    B, N, M, steps = 24, 20, 20, 10
+    dt = 1.0 / N
+    K = steps + N + 3
+    traj = T.random_smooth_trajectories(B, K, dt, seed=9)
+    par = T.random_smooth_params(B, K, dt, seed=9)
+    loops = []
+    for src in (torch.as_tensor(traj), T.DeviceReference(T.KIND_SINUSOIDS, par, K, dt)):
+        quad = Quadrotor3D(drag=True, batch=B).set_hummingbird_params()
+        gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B)
+        opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe)
+        loops.append(ClosedLoop(quad, opt, src, torch.as_tensor(traj[:, 0, :].copy())))
+        loops[-1].run(steps)
+    torch.cuda.synchronize()
+    assert x_rel(loops[1].x.cpu().numpy(), loops[0].x.cpu().numpy()) < 1e-8
+    assert u_rel(loops[1].u0.cpu().numpy(), loops[0].u0.cpu().numpy()) < 1e-8
+
+
+def test_set_reference_state_constant_reference():
+    """quad_optimizer.set_reference_state (quad_opt.py:271-292): constant target over the horizon, default hover inputs
+    0.16 and default target [0,0,0,1,0,...]; the solve against it equals the oracle's"""
+    Quadrotor3D, quad_optimizer, _ = _pkg()
+    N, dt = 10, 0.1
+    quadp = orc.quad_hummingbird()
+    opt = quad_optimizer(Quadrotor3D(drag=True).set_hummingbird_params(), t_horizon=1.0, n_nodes=N)
+    yref, yref_N = opt.set_reference_state()
+    assert yref.shape == (N, 17) and np.array_equal(yref[:, :13], np.tile([0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0], (N, 1)))
+    assert np.all(yref[:, 13:] == 0.16) and np.array_equal(yref_N, yref[-1, :13])
+    x_target = np.array([1.0, -2.0, 3.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    u_target = np.array([0.2, 0.25, 0.3, 0.35])
+    yref, yref_N = opt.set_reference_state(x_target, u_target)
+    assert np.array_equal(yref, np.tile(np.concatenate([x_target, u_target]), (N, 1))) and np.array_equal(yref_N, x_target)
+    x0 = np.array([0.5, -1.5, 2.5, 1.0, 0, 0, 0, 0.2, 0, -0.1, 0, 0, 0])
+    x_opt, w_opt, _, cost = opt.run_optimization(x0)
+    xit, uit = np.zeros((N + 1, 13)), np.zeros((N, 4))
+    r = orc.rti_step(quadp, dt, N, x0, np.ascontiguousarray(yref), x_target.copy(), xit, uit)
+    assert r["status"] == 0
+    assert u_rel(w_opt, uit) < TOL_U64 and x_rel(x_opt, xit) < TOL_X64
+    assert abs(cost - r["cost"]) < 1e-7 * max(1.0, abs(r["cost"]))
+
+
+def test_cold_handle_runs_no_warm_rounds():
+    """warm_start_rounds < 0: every OCP of every solve takes the cold IPM, in the screening + dense mapping too
+    (the dense kernel used to continue up to 8 warm rounds from the active set of its previous solve)"""
+    B, N, M = 40, 20, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(M)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=4, amp_choices=(8.0, 2.0))
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    for variant in (1, 2):
+        gpe = GPEnsemble.fromrange([(gp.X[d, 0], gp.X[d, -1]) for d in range(3)], [gp.M] * 3, theta=list(gp.theta[0]), batch=B)
+        opt = quad_optimizer(Quadrotor3D(drag=True, batch=B).set_hummingbird_params(), t_horizon=1.0, n_nodes=N, gpe=gpe,
+                             warm_start_rounds=-1, solver_variant=variant)
+        opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
+        from mpc_quad_ros_b200 import _capi
+        yref = torch.as_tensor(sc["yref"], device=opt.device).contiguous()
+        yref_e = torch.as_tensor(sc["yref_e"], device=opt.device).contiguous()
+        _capi.check(_capi.lib().qmpc_set_yref(opt._h, _capi.ptr(yref), _capi.ptr(yref_e), _capi.stream_ptr()))
+        opt.set_rgp_params(torch.as_tensor(sc["mu"]))
+        x0 = torch.as_tensor(sc["x0"], device=opt.device)
+        for rep in range(3):        # the second and third solve have a remembered active set available: it must be ignored
+            x_opt, w_opt, _, cost = opt.run_optimization(x0)
+            st, it = opt.solver_status()
+            assert (st == 0).all() and (it > 0).all(), (variant, rep, it.min().item())
+        xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
+        # first solve of a fresh handle with the same data = the oracle's single RTI step
+        opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
+        x_opt, w_opt, _, cost = opt.run_optimization(x0)
+        assert u_rel(w_opt.cpu().numpy(), uo) < TOL_U64 and x_rel(x_opt.cpu().numpy(), xo) < TOL_X64
+
+
+def test_fused_step_uses_rgp_means_only_after_first_regress():
+    """reference: the solver parameters are zeros until the first regress pushes the means (quad_opt.py:101,402-404),
+    also when the ensemble was built with non-zero means (frombasisvectors).  The fused qmpc_step and the method-by-method
+    path agree on the very first solve."""
+    Quadrotor3D, quad_optimizer, GPEnsemble = _pkg()
+    B, N, M = 6, 10, 10
+    dt = 1.0 / N
+    quadp = orc.quad_hummingbird()
+    gp = make_gp(M)
+    sc = random_ocp_batch(B, N, dt, quadp, gp, seed=12, amp_choices=(2.0,))
+    X = [gp.X[d] for d in range(3)]
+    y = [0.4 * np.sin(0.3 * X[d]) for d in range(3)]                     # non-zero prior means
+    Cs = [orc.rgp_prior(gp.X[d], gp.theta[d])[0] for d in range(3)]
+    u_first = []
+    for fused in (True, False):
+        gpe = GPEnsemble.frombasisvectors(X, y, Cs, [list(gp.theta[d]) for d in range(3)], batch=B)
+        opt = quad_optimizer(Quadrotor3D(drag=True, batch=B).set_hummingbird_params(), t_horizon=1.0, n_nodes=N, gpe=gpe)
+        opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
+        x_ref = torch.as_tensor(sc["yref"][:, :, :13].copy(), device=opt.device)
+        x0 = torch.as_tensor(sc["x0"], device=opt.device)
+        if fused:
+            xpp = torch.zeros((B, 13), dtype=torch.float64, device=opt.device)
+            u0 = torch.empty((B, 4), dtype=torch.float64, device=opt.device)
+            opt.step(x0, x_ref, xpp, True, u0)
+            u_first.append(u0.cpu().numpy())
+        else:
+            opt.set_reference_trajectory(x_ref)
+            _, w_opt, _, _ = opt.run_optimization(x0)
+            u_first.append(w_opt[:, 0].cpu().numpy())
+    # oracle: nominal model (alpha = 0) on the first solve
+    xo, uo, _, _ = oracle_solve_batch(dict(sc, alpha=np.zeros_like(sc["alpha"])), quadp, dt, N, gp)
+    assert np.abs(u_first[0] - u_first[1]).max() < 1e-9
+    assert u_rel(u_first[0], uo[:, 0]) < TOL_U64

@@ -158,3 +158,27 @@ def test_emulated_cold_handle_never_uses_the_remembered_active_set(variant):
     assert u_rel(u2, uo) < TOL[variant] and x_rel(x2, xo) < TOL[variant]
     if variant == 2:
         assert r2["hard"] == B          # nothing was screened
+
+
+@VARIANTS
+def test_emulated_build_without_tile_ring_matches_oracle(variant):
+    """the default build streams the stage tiles through a shared-memory ring (QMPC_RING=2, padded tile rows QMPC_WR=18);
+    the A/B flavour without the ring (tiles read in place, unpadded rows) lands on the same minimiser from a cold solve
+    and from the warm-started second solve"""
+    B, N = 3, 20
+    dt = 1.0 / N
+    quad = orc.quad_hummingbird()
+    gp = make_gp(20)
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=3, amp_choices=(8.0, 2.0))
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
+    xo, uo, _, _ = oracle_solve_batch(sc, quad, dt, N, gp)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=variant, flavour="noring")
+    assert (r1["status"] == 0).all() and u_rel(ue, uo) < TOL[variant] and x_rel(xe, xo) < TOL[variant]
+    sc2 = dict(sc)
+    sc2["x0"] = sc["x0"] + 0.01 * np.random.default_rng(1).standard_normal(sc["x0"].shape)
+    sc2["xit"], sc2["uit"] = xe.copy(), ue.copy()
+    xo2, uo2, _, _ = oracle_solve_batch(sc2, quad, dt, N, gp)
+    x2, u2 = xe.copy(), ue.copy()
+    r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=r1["act"].copy(), variant=variant, flavour="noring")
+    assert (r2["status"] == 0).all() and u_rel(u2, uo2) < TOL[variant] and x_rel(x2, xo2) < TOL[variant]

@@ -148,3 +148,20 @@ def test_rgp_learn_matches_reference_code(golden, tag):
         mu_z, C_z = orc.rgp_learn(X, mu_g, C_g, mu_eta, C_eta, C_g_eta, Kxi, xt, yt)
         for name, val in (("mu_z", mu_z), ("C_z", C_z), ("mu_g", mu_g), ("C_g", C_g), ("mu_eta", mu_eta), ("C_eta", C_eta), ("Kx_inv", Kxi)):
             assert rel_err(val, g[f"learn_{tag}_{name}"][t]) < 1e-11, (tag, t, name)
+
+
+def test_numpy_rgp_restatement_vs_reference_code(golden):
+    """oracle/rgp_numpy.py (the 'reference numpy RGP, 1 core' timing leg of bench.py) reproduces the outputs of the
+    reference's own RGP class (tests/golden/reference_code.npz, generated from /root/reference by oracle/make_golden.py)"""
+    from oracle.rgp_numpy import NumpyRGP
+    g = golden("reference_code")
+    for tag in ("m20", "m7"):
+        X, th = g[f"rgp_{tag}_X"], g[f"rgp_{tag}_theta"]
+        xt, yt = g[f"rgp_{tag}_xt"], g[f"rgp_{tag}_yt"]
+        models = [NumpyRGP(X[d], th[d]) for d in range(3)]
+        assert rel_err(np.stack([m.K_x_inv for m in models]), g[f"rgp_{tag}_Kx_inv"]) < 1e-12
+        for t in range(len(xt)):
+            for d in range(3):
+                models[d].regress(xt[t, d:d + 1], yt[t, d:d + 1])
+            assert rel_err(np.stack([m.mu for m in models]), g[f"rgp_{tag}_mu"][t]) < 1e-12
+            assert rel_err(np.stack([m.C for m in models]), g[f"rgp_{tag}_C"][t]) < 1e-12
