@@ -201,6 +201,12 @@ int qrgp_shared_apply(qrgp_handle_t g, const double *info, void *stream);
 int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double *x_now, const double *x_ref,
               double *x_pred_prev, int first_step, double *u0_out, void *stream);
 
+/* the ROS node's variant of the same step (src/mpc_controller_node.py:298,315): the nominal prediction and the drag
+ * residual use the odometry period instead of the OCP's dt (odometry_dt <= 0 -> the OCP's dt = qmpc_step); the caller cuts
+ * x_ref with skip = control_freq_factor (qmpc_reference_chunk / qmpc_reference_generate, node :278) */
+int qmpc_step_dt(qmpc_handle_t h, qrgp_handle_t g, const double *x_now, const double *x_ref,
+                 double *x_pred_prev, int first_step, double *u0_out, double odometry_dt, void *stream);
+
 /* the whole closed-loop step in one call: qmpc_reference_chunk(traj, idx) -> qmpc_step -> qmpc_plant_period(x, u0).
  * traj [B][K][13]; x [B][13] plant state in/out; chunk [B][N][13] and u0 [B][4] caller-owned scratch/outputs. */
 int qmpc_closed_loop_step(qmpc_handle_t h, qrgp_handle_t g, const double *traj, int K, int idx, double *x,

@@ -675,7 +675,14 @@ int qrgp_shared_apply(qrgp_handle_t g, const double* info, void* stream)
 int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const double* x_ref, double* x_pred_prev,
               int first_step, double* u0_out, void* stream)
 {
+    return qmpc_step_dt(h, g, x_now, x_ref, x_pred_prev, first_step, u0_out, 0.0, stream);
+}
+
+int qmpc_step_dt(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const double* x_ref, double* x_pred_prev,
+                 int first_step, double* u0_out, double odometry_dt, void* stream)
+{
     if (!h || !x_now || !x_ref || !x_pred_prev) return fail(QMPC_ERR_ARG, "null argument");
+    const double pred_dt = odometry_dt > 0 ? odometry_dt : h->dt;
     const int B = h->cfg.batch, N = h->cfg.n_nodes;
     if (g && (g->M != h->cfg.n_basis || (g->B != B && g->B != 1)))
         return fail(QMPC_ERR_ARG, "RGP handle does not match the solver (n_basis / batch)");
@@ -694,7 +701,7 @@ int qmpc_step(qmpc_handle_t h, qrgp_handle_t g, const double* x_now, const doubl
     const bool per_vehicle = g && g->B == B;
     double* xt = per_vehicle ? g->xt : h->xt;
     double* yt = per_vehicle ? g->yt : h->yt;
-    post_solve_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(h->mp64, B, h->dt, first_step, x_now, h->u0, x_pred_prev,
+    post_solve_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(h->mp64, B, pred_dt, first_step, x_now, h->u0, x_pred_prev,
                                                            g ? xt : nullptr, g ? yt : nullptr);
     LAUNCH_CHECK();
     if (per_vehicle) { rc = regress_launch(g, xt, yt, stream); if (rc) return rc; }

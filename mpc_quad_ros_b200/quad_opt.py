@@ -219,10 +219,12 @@ class quad_optimizer:
         return mu_g_t, C_g_t
 
     # ---- fused closed-loop step (execute_trajectory.py:196-277 in one call, all on the GPU) ------------------------------
-    def step(self, x_now, x_ref, x_pred_prev, first_step, u0_out=None, rgp=True):
+    def step(self, x_now, x_ref, x_pred_prev, first_step, u0_out=None, rgp=True, odometry_dt=None):
         """reference chunk -> solve -> u0 -> nominal prediction -> residual -> RGP regress -> alpha for the next solve.
         x_now [B,13], x_ref [B,N,13], x_pred_prev [B,13] (updated in place), u0_out [B,4] (optional) CUDA tensors.
         rgp=False: solve and prediction only (the RGP update of this step is run elsewhere, swarm.SharedSwarmRGP.begin)."""
         g = self.gpe._h if (self.gpe is not None and rgp) else C.c_void_p(0)
-        _capi.check(_capi.lib().qmpc_step(self._h, g, _capi.ptr(x_now), _capi.ptr(x_ref), _capi.ptr(x_pred_prev),
-                                          int(bool(first_step)), _capi.ptr(u0_out), self._s()))
+        # odometry_dt: the ROS node predicts and differences over the odometry period (mpc_controller_node.py:298,315)
+        _capi.check(_capi.lib().qmpc_step_dt(self._h, g, _capi.ptr(x_now), _capi.ptr(x_ref), _capi.ptr(x_pred_prev),
+                                             int(bool(first_step)), _capi.ptr(u0_out),
+                                             C.c_double(0.0 if odometry_dt is None else float(odometry_dt)), self._s()))

@@ -66,7 +66,7 @@ def random_smooth_trajectories(B, K, dt, seed=1234, v_max=10.0, z0=3.0, a_max=No
     return out
 
 
-def lemniscate_trajectories(B, K, dt, v_peak=15.0, a=10.0, z0=3.0, seed=1234):
+def lemniscate_trajectories(B, K, dt, v_peak=15.0, a=10.0, z0=3.0, seed=1234, ramp=3.0):
     """BASELINE config 5: p = (a sin wt, a sin wt cos wt, z0), w chosen so that the peak speed is v_peak
     (thrust limits active); vehicles differ by a random phase and heading."""
     t = np.arange(K) * dt
@@ -75,8 +75,8 @@ def lemniscate_trajectories(B, K, dt, v_peak=15.0, a=10.0, z0=3.0, seed=1234):
     for b in range(B):
         rng = np.random.Generator(np.random.Philox(key=seed + b))
         ph, yaw = rng.uniform(0, 2 * np.pi), rng.uniform(0, 2 * np.pi)
-        th = ph + w * np.where(t < 3.0, t * t / 6.0, t - 1.5)      # angular rate ramps 0 -> w over 3 s (start from rest)
-        dth = w * np.where(t < 3.0, t / 3.0, 1.0)
+        th = ph + w * np.where(t < ramp, t * t / (2.0 * ramp), t - 0.5 * ramp)      # angular rate ramps 0 -> w over `ramp` s (start from rest)
+        dth = w * np.where(t < ramp, t / ramp, 1.0)
         px, py = a * np.sin(th), a * np.sin(th) * np.cos(th)
         vx, vy = a * np.cos(th) * dth, a * np.cos(2 * th) * dth
         c, s = np.cos(yaw), np.sin(yaw)

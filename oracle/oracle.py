@@ -143,6 +143,25 @@ def rti_step(quad, dt, N, x0, yref, yref_e, xit, uit, gp=None, alpha=None, Wd=W_
     return out
 
 
+def rti_step_batch(quad, dt, N, x0, yref, yref_e, xit, uit, gp=None, alpha=None, Wd=W_DIAG, Wed=WE_DIAG,
+                   lbu=0.0, ubu=1.0, mu_tol=1e-13, max_iter=60, polish=True, nthreads=0):
+    """B independent RTI steps (OpenMP over vehicles).  x0 [B,13], yref [B,N,17], yref_e [B,13]; xit [B,N+1,13] and
+    uit [B,N,4] are updated IN PLACE; alpha [B,3,M] or [3,M] (shared).  returns dict(status [B], cost [B], iters [B], bad)"""
+    B = x0.shape[0]
+    assert xit.shape == (B, N + 1, NX) and uit.shape == (B, N, NU) and xit.flags.c_contiguous and uit.flags.c_contiguous
+    M = gp.M if gp is not None else 0
+    cost, iters, status = np.empty(B), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    stride = 0
+    if alpha is not None:
+        alpha = _c(alpha)
+        stride = 3 * M if alpha.ndim == 3 else 0
+    bad = lib().orc_rti_step_batch(_p(quad), _d(dt), N, M, _p(gp.X if gp else None), _p(gp.theta if gp else None),
+                                   _p(alpha), int(stride), _p(_c(Wd)), _p(_c(Wed)), _d(lbu), _d(ubu), int(B),
+                                   _p(_c(x0)), _p(_c(yref)), _p(_c(yref_e)), _p(xit), _p(uit), _p(cost), _pi(iters), _pi(status),
+                                   _d(mu_tol), int(max_iter), int(polish), int(nthreads))
+    return dict(status=status, cost=cost, iters=iters, bad=bad)
+
+
 def make_yref(x_ref_chunk, u_ref=0.16):
     """quad_opt.py:295-317: yref[j] = [x_ref[j], u_ref*1_4]; yref_N = x_ref[-1]."""
     x_ref_chunk = np.asarray(x_ref_chunk, dtype=np.float64)

@@ -977,6 +977,31 @@ int orc_closed_loop(const double *quad, const double *plant, double dt, double s
     return bad;
 }
 
+/* B independent RTI steps (one per vehicle, OpenMP over vehicles): the per-step parity reference for a batch with
+ * injected iterates.  Arrays are vehicle-major like the C-ABI of the library; alpha may be NULL (M == 0); alpha_stride
+ * doubles between vehicles (0 = one shared model).  status/iters/cost per vehicle. */
+int orc_rti_step_batch(const double *quad, double dt, int N, int M, const double *gpX, const double *gpth,
+                       const double *alpha, int alpha_stride, const double *Wd, const double *Wed, double lbu, double ubu,
+                       int B, const double *x0, const double *yref, const double *yref_e, double *xit, double *uit,
+                       double *cost, int *iters, int *status, double mu_tol, int max_iter, int do_polish, int nthreads)
+{
+    int bad = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : bad)
+    for (int b = 0; b < B; ++b) {
+        double kkt;
+        int st = orc_rti_step(quad, dt, N, M, gpX, gpth, alpha ? alpha + (size_t)b * alpha_stride : NULL, Wd, Wed, lbu, ubu,
+                              x0 + (size_t)b * NX, yref + (size_t)b * N * NZ, yref_e + (size_t)b * NX,
+                              xit + (size_t)b * (N + 1) * NX, uit + (size_t)b * N * NU, cost + b, iters + b, &kkt,
+                              mu_tol, max_iter, do_polish, NULL);
+        status[b] = st;
+        if (st > 1) bad += 1;
+    }
+    return bad;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP
