@@ -9,6 +9,7 @@
 #else
 #include <cuda_runtime.h>
 #define QMPC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define QMPC_STATIC_SMEM(type, name, count) __shared__ type name[count]
 #endif
 
 namespace qmpc {

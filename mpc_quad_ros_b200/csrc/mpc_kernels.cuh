@@ -45,26 +45,64 @@ struct LinArgs {
     real* W;              // [B][N][13][16]
 };
 
-// GP mean/slope per body axis; the 3*M kernel evaluations are spread over the 16 lanes of the group.
+// GP mean/slope per body axis.  Five lanes of the 16-lane group work on each axis (lane j: axis j / 5, basis points
+// j % 5, j % 5 + 5, ...; lane 15 idles), so a lane's kernel width / amplitude are fixed and nothing is selected or divided
+// per point.  A lane's basis points and weights do not change over the four RK4 stages: for M <= 20 they are fetched once
+// into registers (GpLane), larger M re-read them (L1) every stage.
+constexpr int GP_LPA = 5;          // lanes per axis
+constexpr int GP_REG = 4;          // basis points per lane kept in registers (M <= GP_LPA * GP_REG)
+
 template <typename real>
-__device__ __forceinline__ void gp_group_eval(const ModelParams<real>& mp, unsigned hmask, int j,
+struct GpLane {
+    int d, l;                      // axis (3 = idle lane), first basis point
+    real il2;                      // 1/L^2 of the axis
+    real* xb;                      // shared memory, stride blockDim.x: GP_REG basis points, then GP_REG weights sf^2 * alpha
+};
+
+template <typename real>
+__device__ __forceinline__ void gp_lane_setup(const ModelParams<real>& mp, int j, const double* __restrict__ gpX,
+                                              const double* __restrict__ alpha, real* lane_store, GpLane<real>& g)
+{
+    g.xb = lane_store;
+    g.d = j / GP_LPA; g.l = j - g.d * GP_LPA;
+    const int d = g.d < 3 ? g.d : 0;
+    g.il2 = d == 0 ? mp.iL2[0] : (d == 1 ? mp.iL2[1] : mp.iL2[2]);
+    const real sf2 = d == 0 ? mp.sf2[0] : (d == 1 ? mp.sf2[1] : mp.sf2[2]);
+#pragma unroll
+    for (int t = 0; t < GP_REG; ++t) {
+        const int i = g.l + GP_LPA * t;
+        const bool on = g.d < 3 && i < mp.M;
+        g.xb[t * blockDim.x] = on ? real(__ldg(gpX + d * mp.M + i)) : real(0);
+        g.xb[(GP_REG + t) * blockDim.x] = on ? sf2 * real(__ldg(alpha + d * mp.M + i)) : real(0);
+    }
+}
+
+template <typename real>
+__device__ __forceinline__ void gp_group_eval(const ModelParams<real>& mp, unsigned hmask, const GpLane<real>& g,
                                               const double* __restrict__ gpX, const double* __restrict__ alpha,
                                               const real* vb, real* mu, real* dmu)
 {
-    real s0 = 0, s1 = 0, s2 = 0, d0 = 0, d1 = 0, d2 = 0;
-    const int M = mp.M, tot = 3 * M;
-    for (int p = j; p < tot; p += 16) {
-        const int d = p / M;
-        const real v = d == 0 ? vb[0] : (d == 1 ? vb[1] : vb[2]);
-        const real il2 = d == 0 ? mp.iL2[0] : (d == 1 ? mp.iL2[1] : mp.iL2[2]);
-        const real sf2 = d == 0 ? mp.sf2[0] : (d == 1 ? mp.sf2[1] : mp.sf2[2]);
-        const real e = v - real(__ldg(gpX + p));
-        const real ka = sf2 * rexp<real>(real(-0.5) * e * il2 * e) * real(__ldg(alpha + p));
-        const real dk = ka * (-e * il2);
-        if (d == 0) { s0 += ka; d0 += dk; } else if (d == 1) { s1 += ka; d1 += dk; } else { s2 += ka; d2 += dk; }
+    const real v = g.d == 0 ? vb[0] : (g.d == 1 ? vb[1] : vb[2]);
+    real s = 0, ds = 0;
+    if (mp.M <= GP_LPA * GP_REG) {
+#pragma unroll
+        for (int t = 0; t < GP_REG; ++t) {
+            const real e = v - g.xb[t * blockDim.x];
+            const real ka = g.xb[(GP_REG + t) * blockDim.x] * rexp<real>(real(-0.5) * e * g.il2 * e);
+            s += ka; ds -= ka * e * g.il2;
+        }
+    } else if (g.d < 3) {
+        const real sf2 = g.d == 0 ? mp.sf2[0] : (g.d == 1 ? mp.sf2[1] : mp.sf2[2]);
+        const double* X = gpX + g.d * mp.M;
+        const double* al = alpha + g.d * mp.M;
+        for (int i = g.l; i < mp.M; i += GP_LPA) {
+            const real e = v - real(__ldg(X + i));
+            const real ka = sf2 * real(__ldg(al + i)) * rexp<real>(real(-0.5) * e * g.il2 * e);
+            s += ka; ds -= ka * e * g.il2;
+        }
     }
-    mu[0] = half_sum(hmask, s0); mu[1] = half_sum(hmask, s1); mu[2] = half_sum(hmask, s2);
-    dmu[0] = half_sum(hmask, d0); dmu[1] = half_sum(hmask, d1); dmu[2] = half_sum(hmask, d2);
+    mu[0] = half_sum(hmask, g.d == 0 ? s : real(0)); mu[1] = half_sum(hmask, g.d == 1 ? s : real(0)); mu[2] = half_sum(hmask, g.d == 2 ? s : real(0));
+    dmu[0] = half_sum(hmask, g.d == 0 ? ds : real(0)); dmu[1] = half_sum(hmask, g.d == 1 ? ds : real(0)); dmu[2] = half_sum(hmask, g.d == 2 ? ds : real(0));
 }
 
 template <typename real>
@@ -88,6 +126,9 @@ __global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real> a)
 #pragma unroll
     for (int i = 0; i < NX; ++i) { kprev[i] = 0; dkprev[i] = 0; accx[i] = x[i]; accd[i] = (i == sj) ? real(1) : real(0); }
     const real zero3[3] = {0, 0, 0};
+    GpLane<real> gl;
+    QMPC_STATIC_SMEM(real, gp_store, 2 * GP_REG * 128);       // per thread: its basis points and weights (only the thread itself reads them)
+    if (a.mp.M > 0) gp_lane_setup(a.mp, j, a.gpX, al, gp_store + threadIdx.x, gl);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
@@ -98,7 +139,7 @@ __global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real> a)
         if (a.mp.M > 0) {
             real vb[3];
             body_velocity(xs, vb);
-            gp_group_eval(a.mp, hmask, j, a.gpX, al, vb, mu, dmu);
+            gp_group_eval(a.mp, hmask, gl, a.gpX, al, vb, mu, dmu);
         } else {
 #pragma unroll
             for (int i = 0; i < 3; ++i) { mu[i] = zero3[i]; dmu[i] = zero3[i]; }

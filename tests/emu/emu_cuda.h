@@ -87,6 +87,8 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
 #define blockDim (emu::t_blockDim)
 #define gridDim (emu::t_gridDim)
 #define QMPC_DYN_SMEM(name) unsigned char* name = emu::t_smem
+// static shared array: one per block; the emulation runs blocks one after the other, so one process-wide array per call site
+#define QMPC_STATIC_SMEM(type, name, count) static type name[count]
 
 template <typename T> inline T __shfl_sync(unsigned m, T v, int src) { return emu::shfl(m, v, src); }
 template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return emu::shfl(m, v, emu::t_lane ^ x); }
