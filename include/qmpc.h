@@ -79,7 +79,7 @@ typedef struct {
                               is busy when the previous step left more than screen_busy_pct % of the vehicles unsettled
                               after screen_rounds rounds (start-up transients, aggressive references): the dense launch
                               would need several waves then, and a Riccati round is cheaper than the dense condensing */
-    int screen_busy_pct;   /* 0 -> 20 */
+    int screen_busy_pct;   /* 0 -> 25 */
 } qmpc_config;
 
 const char *qmpc_last_error(void);

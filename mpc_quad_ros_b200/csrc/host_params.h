@@ -81,7 +81,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.bail_changed = c.bail_changed > 0 ? c.bail_changed : (1 << 20);
     a.final_rollout = c.final_rollout > 0 ? 1 : 0;
     a.dense_warm_rounds = 0;
-    a.warm_rounds_busy = 0; a.bail_round_busy = a.bail_round; a.busy_threshold = 1 << 30; a.skip_screen_iters = 0;
+    a.warm_rounds_busy = 0; a.bail_round_busy = a.bail_round; a.busy_threshold = 1 << 30; a.skip_screen_iters = 0; a.bail_to_ipm = 0;
     a.unsettled_prev = nullptr; a.unsettled_cur = nullptr;
     a.timeline = nullptr; a.hard_list = nullptr; a.hard_count = nullptr;
 }
@@ -107,9 +107,10 @@ inline void fill_screen_args(const qmpc_config& c, IpmArgs<real>& a)
         a.warm_rounds = screen;
         a.warm_rounds_busy = c.screen_rounds_busy < 0 ? 0 : (c.screen_rounds_busy == 0 ? 8 : c.screen_rounds_busy);
         a.bail_round_busy = a.bail_round > 3 ? a.bail_round : 3;
-        const int pct = c.screen_busy_pct > 0 ? c.screen_busy_pct : 20;
+        const int pct = c.screen_busy_pct > 0 ? c.screen_busy_pct : 25;
         a.busy_threshold = (int)((long long)c.batch * pct / 100);
         a.skip_screen_iters = 12;
+        a.bail_to_ipm = 0;       // measured (profiles/r02_policy_ab.txt): sending given-up OCPs straight to the dense IPM costs 3 %
     }
     a.smem_per_warp = ipm_smem_reals(c.n_nodes, false, sizeof(real) == 8);
     a.ring_off = ipm_ring_off(c.n_nodes, false);

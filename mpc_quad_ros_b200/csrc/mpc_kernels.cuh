@@ -182,6 +182,7 @@ struct IpmArgs {
     int dense_warm_rounds;         // dense kernel: active-set rounds from the handed-over guess before the IPM; 0 = IPM first
     int warm_rounds_busy;          // screening mode: round limit of a busy step (see unsettled_prev); 0 = warm_rounds
     int bail_round_busy;           // bail_round of a busy step
+    int bail_to_ipm;               // screening mode: an OCP whose rounds gave up (cycle, not contracting) skips the dense kernel's warm rounds
     int skip_screen_iters;         // screening mode: previous-solve IPM iterations from which an OCP skips the rounds (0 = never)
     int busy_threshold;            // a step is busy when the previous step left more than this many OCPs unsettled after warm_rounds
     const int* unsettled_prev;     // device counters (previous / this step) of OCPs not settled after warm_rounds rounds, or null
@@ -370,6 +371,7 @@ struct WarpCtx {
     // lane 0 issues one TMA bulk copy per stage (cp.async.bulk + mbarrier, RING - 1 stages ahead of the compute), the warp
     // waits on the slot's barrier and reads the tile with LDS.  Otherwise the tile is read in place (L2/L1, __ldg).
     static constexpr int RING = (sizeof(real) == 8) ? QMPC_RING : 0;
+    bool gave_up;                    // the last refine_rounds ended on a cycle / a non-contracting change count (not on its round limit)
     void* hist_store;                // 6 x 8 bytes: active-set fingerprints of the running attempt (cycle detection)
     real* ring;                      // RING slots of WT reals
     unsigned long long* rbar;        // one mbarrier per slot
@@ -709,6 +711,7 @@ struct WarpCtx {
                                   int mark_round = -1, int* mark_counter = nullptr)
     {
         int prev_changed = 1 << 30;
+        gave_up = false;
         ActiveSetHistory hist;
         hist.init(hist_store);
         for (int round = 0; round < max_rounds; ++round) {
@@ -740,9 +743,9 @@ struct WarpCtx {
             if (!changed) return true;
             const bool cycling = hist.seen_then_push(fp, lane);   // the deterministic iteration met this active set before: it cycles
             if ((round + 1 == mark_round || (cycling && round + 1 < mark_round)) && mark_counter && lane == 0) atomicAdd(mark_counter, 1);
-            if (cycling) return false;
-            if (may_bail && round >= bail_round && changed >= prev_changed) return false;   // not contracting: leave it to the IPM
-            if (may_bail && round >= 1 && changed > a.bail_changed) return false;
+            if (cycling) { gave_up = true; return false; }
+            if (may_bail && round >= bail_round && changed >= prev_changed) { gave_up = true; return false; }   // not contracting: leave it to the IPM
+            if (may_bail && round >= 1 && changed > a.bail_changed) { gave_up = true; return false; }
             prev_changed = changed;
         }
         return false;
@@ -874,6 +877,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     c.ring = sm + a.ring_off + HIST_REALS<real>();
     c.rbar = reinterpret_cast<unsigned long long*>(c.ring + WarpCtx<real>::RING * WT);
     c.rphase = 0;
+    c.gave_up = false;
     if (WarpCtx<real>::RING) {
         if (lane == 0) for (int s_ = 0; s_ < WarpCtx<real>::RING; ++s_) mbar_init(c.rbar + s_, 1);
         __syncwarp();
@@ -924,7 +928,9 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
             was_known = warp_max(int(!was_known)) == 0;
             if (was_known) for (int e = lane; e < E; e += 32) act[e] = c.fx[e] == real(1) ? 1 : (c.fx[e] == real(2) ? 2 : 0);
         }
-        if (long_ipm_last_time) for (int e = lane; e < E; e += 32) act[e] = 255;    // the dense kernel starts from its IPM
+        // the dense kernel continues the rounds from the guess they ended on - unless they ended on a cycle or stopped
+        // contracting (or last step's solve was a long IPM run): more rounds will not settle, it starts its IPM at once
+        if (long_ipm_last_time || (a.bail_to_ipm && c.gave_up)) for (int e = lane; e < E; e += 32) act[e] = 255;
         if (lane == 0) { a.rounds[ocp] = rounds; a.hard_list[atomicAdd(a.hard_count, 1)] = ocp; }
         return;
     }
