@@ -272,7 +272,7 @@ template <typename real>
 static int solve_impl(qmpc_solver* h, void* stream)
 {
     const int B = h->cfg.batch, N = h->cfg.n_nodes;
-    LinArgs<real> la;
+    LinArgs<double, real> la;       // the linearisation always runs in fp64; fp32 handles store fp32 tiles (see LinArgs)
     fill_lin_args(h->cfg, la);
     la.xit = h->xit; la.uit = h->uit; la.yref = h->yref; la.alpha = h->alpha_src; la.alpha_stride = h->alpha_stride;
     la.gpX = h->gpX; la.W = static_cast<real*>(h->W);
@@ -286,7 +286,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
         reset_failed_kernel<<<cdiv((long long)B * (N + 1), 256), 256, 0, S(stream)>>>(B, N, h->status, h->yref, h->yref_e, h->xit, h->uit, h->act, h->fail_streak);
         LAUNCH_CHECK();
     }
-    qmpc_linearize_kernel<real><<<cdiv((long long)B * N * 16, 128), 128, 0, S(stream)>>>(la);
+    qmpc_linearize_kernel<double, real><<<cdiv((long long)B * N * 16, 128), 128, 0, S(stream)>>>(la);
     LAUNCH_CHECK();
     if (e1) CU_TRY(cudaEventRecord(e1, S(stream)));
     IpmArgs<real> ia;

@@ -36,11 +36,15 @@ inline int ipm_smem_reals(int N, bool full, bool fp64)
     const int ring = fp64 ? QMPC_RING : 0;
     const int hist = fp64 ? HIST_REALS<double>() : HIST_REALS<float>();
     const int mbar = fp64 ? ring : 2 * ring;
-    return (ipm_ring_off(N, full) + hist + ring * WT + mbar + 1) & ~1;
+    const int refine = fp64 ? 0 : 2 * ((N + 1) * 13 + 16 + 4 * N);  // fp32 handles: (N+1) x 13 + 16 + 4N doubles of refinement scratch
+    return (ipm_ring_off(N, full) + hist + ring * WT + mbar + refine + 3) & ~3;
+}
+// fp32 handles: offset (in floats, 8-byte aligned) of the fp64 refinement scratch = right after the fingerprint history
+inline int ipm_refine_off(int N, bool full) { return ipm_ring_off(N, full) + HIST_REALS<float>();
 }
 
-template <typename real>
-inline void fill_lin_args(const qmpc_config& c, LinArgs<real>& a)
+template <typename real, typename treal>
+inline void fill_lin_args(const qmpc_config& c, LinArgs<real, treal>& a)
 {
     a.B = c.batch; a.N = c.n_nodes; a.dt = real(cfg_dt(c));
     fill_model(c, a.mp);
@@ -77,6 +81,7 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     a.warm_rounds = (c.warm_start_rounds < 0 || a.max_refine == 0) ? 0 : (c.warm_start_rounds == 0 ? 6 : c.warm_start_rounds);
     a.smem_per_warp = ipm_smem_reals(c.n_nodes, true, f64);
     a.ring_off = ipm_ring_off(c.n_nodes, true);
+    a.refine_off = f64 ? 0 : ipm_refine_off(c.n_nodes, true);
     a.bail_round = c.bail_round > 0 ? c.bail_round : 2;
     a.bail_changed = c.bail_changed > 0 ? c.bail_changed : (1 << 20);
     a.final_rollout = c.final_rollout > 0 ? 1 : 0;
@@ -114,6 +119,7 @@ inline void fill_screen_args(const qmpc_config& c, IpmArgs<real>& a)
     }
     a.smem_per_warp = ipm_smem_reals(c.n_nodes, false, sizeof(real) == 8);
     a.ring_off = ipm_ring_off(c.n_nodes, false);
+    a.refine_off = 0;
 }
 
 }  // namespace qmpc

@@ -30,7 +30,11 @@ constexpr int WR = QMPC_WR;
 constexpr int WT = 13 * WR;  // reals per stage tile
 constexpr int FAC = 72;      // reals per stage factor record: Lx[13][4], lg[4], Lam[10], lgc[4], pad[2]
 
-template <typename real>
+// real = arithmetic of the RK4 / sensitivity propagation, treal = storage type of the stage tiles.  fp32 handles run
+// <double, float>: the defect b = Phi - x_{k+1} and the gradient q = dt W (x - xref) are differences of O(10) quantities -
+// formed in fp32 they carry 1e-6 absolute noise that the feedback gains turn into 1e-4..1e-2 of control error; formed in
+// fp64 and rounded once, their error is relative to their own (small) size.
+template <typename real, typename treal = real>
 struct LinArgs {
     int B, N;
     real dt;
@@ -42,7 +46,7 @@ struct LinArgs {
     const double* alpha;  // [B][3][M]  (unused when mp.M == 0)
     int alpha_stride;     // doubles between vehicles: 3*M, or 0 when one shared model serves every vehicle
     const double* gpX;    // [3][M]
-    real* W;              // [B][N][13][16]
+    treal* W;             // [B][N][13][16]
 };
 
 // GP mean/slope per body axis.  Five lanes of the 16-lane group work on each axis (lane j: axis j / 5, basis points
@@ -105,8 +109,8 @@ __device__ __forceinline__ void gp_group_eval(const ModelParams<real>& mp, unsig
     dmu[0] = half_sum(hmask, g.d == 0 ? ds : real(0)); dmu[1] = half_sum(hmask, g.d == 1 ? ds : real(0)); dmu[2] = half_sum(hmask, g.d == 2 ? ds : real(0));
 }
 
-template <typename real>
-__global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real> a)
+template <typename real, typename treal = real>
+__global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real, treal> a)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int node = gt >> 4, j = gt & 15;
@@ -158,9 +162,9 @@ __global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real> a)
 #pragma unroll
         for (int i = 0; i < NX; ++i) accd[i] = a.Qd[i] * (x[i] - real(__ldg(yr + i)));
     }
-    real* Wt = a.W + (size_t)node * WT;
+    treal* Wt = a.W + (size_t)node * WT;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) Wt[i * WR + j] = accd[i];
+    for (int i = 0; i < NX; ++i) Wt[i * WR + j] = treal(accd[i]);
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -192,6 +196,7 @@ struct IpmArgs {
     int final_rollout;             // 1: always roll the horizon out at the end (A/B knob)
     int post_bail;                 // 1: the rounds after the IPM may give up early too (fp32: rounding noise can keep them busy)
     int smem_per_warp;             // reals
+    int refine_off;                // fp32 handles: offset (reals) of the fp64 scratch of the iterative refinement, 0 = none
     int ring_off;                  // offset (reals) of the tile ring + its mbarriers inside the per-warp block (QMPC_RING builds)
     const double* x0;              // [B][13]
     const double* yref;            // [B][N][17]
@@ -260,44 +265,52 @@ __device__ __forceinline__ void st2(real* p, real a, real b)
 }
 
 template <typename real>
-struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal
+struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal; inputs / outputs of any floating type, arithmetic in `real`
     real l10, l20, l21, l30, l31, l32, i0, i1, i2, i3;
-    __device__ __forceinline__ void factor(const real* M /* 4x4 row-major, lower used */)
+    template <typename T>
+    __device__ __forceinline__ void factor(const T* M /* 4x4 row-major, lower used */)
     {
-        i0 = rrsqrt<real>(M[0]);
-        l10 = M[4] * i0; l20 = M[8] * i0; l30 = M[12] * i0;
-        i1 = rrsqrt<real>(M[5] - l10 * l10);
-        l21 = (M[9] - l20 * l10) * i1; l31 = (M[13] - l30 * l10) * i1;
-        i2 = rrsqrt<real>(M[10] - l20 * l20 - l21 * l21);
-        l32 = (M[14] - l30 * l20 - l31 * l21) * i2;
-        i3 = rrsqrt<real>(M[15] - l30 * l30 - l31 * l31 - l32 * l32);
+        i0 = rrsqrt<real>(real(M[0]));
+        l10 = real(M[4]) * i0; l20 = real(M[8]) * i0; l30 = real(M[12]) * i0;
+        i1 = rrsqrt<real>(real(M[5]) - l10 * l10);
+        l21 = (real(M[9]) - l20 * l10) * i1; l31 = (real(M[13]) - l30 * l10) * i1;
+        i2 = rrsqrt<real>(real(M[10]) - l20 * l20 - l21 * l21);
+        l32 = (real(M[14]) - l30 * l20 - l31 * l21) * i2;
+        i3 = rrsqrt<real>(real(M[15]) - l30 * l30 - l31 * l31 - l32 * l32);
     }
-    __device__ __forceinline__ void fsolve(const real* v, real* z) const   // Lam z = v
+    template <typename TI, typename TO>
+    __device__ __forceinline__ void fsolve(const TI* v, TO* z) const   // Lam z = v
     {
-        z[0] = v[0] * i0;
-        z[1] = (v[1] - l10 * z[0]) * i1;
-        z[2] = (v[2] - l20 * z[0] - l21 * z[1]) * i2;
-        z[3] = (v[3] - l30 * z[0] - l31 * z[1] - l32 * z[2]) * i3;
+        const real z0 = real(v[0]) * i0;
+        const real z1 = (real(v[1]) - l10 * z0) * i1;
+        const real z2 = (real(v[2]) - l20 * z0 - l21 * z1) * i2;
+        const real z3 = (real(v[3]) - l30 * z0 - l31 * z1 - l32 * z2) * i3;
+        z[0] = TO(z0); z[1] = TO(z1); z[2] = TO(z2); z[3] = TO(z3);
     }
-    __device__ __forceinline__ void bsolve_neg(const real* v, real* u) const   // Lam^T u = -v
+    template <typename TI, typename TO>
+    __device__ __forceinline__ void bsolve_neg(const TI* v, TO* u) const   // Lam^T u = -v
     {
-        u[3] = -v[3] * i3;
-        u[2] = (-v[2] - l32 * u[3]) * i2;
-        u[1] = (-v[1] - l21 * u[2] - l31 * u[3]) * i1;
-        u[0] = (-v[0] - l10 * u[1] - l20 * u[2] - l30 * u[3]) * i0;
+        const real u3 = -real(v[3]) * i3;
+        const real u2 = (-real(v[2]) - l32 * u3) * i2;
+        const real u1 = (-real(v[1]) - l21 * u2 - l31 * u3) * i1;
+        const real u0 = (-real(v[0]) - l10 * u1 - l20 * u2 - l30 * u3) * i0;
+        u[0] = TO(u0); u[1] = TO(u1); u[2] = TO(u2); u[3] = TO(u3);
     }
-    __device__ __forceinline__ void store(real* p) const
+    template <typename TO>
+    __device__ __forceinline__ void store(TO* p) const
     {
-        p[0] = l10; p[1] = l20; p[2] = l21; p[3] = l30; p[4] = l31; p[5] = l32; p[6] = i0; p[7] = i1; p[8] = i2; p[9] = i3;
+        p[0] = TO(l10); p[1] = TO(l20); p[2] = TO(l21); p[3] = TO(l30); p[4] = TO(l31); p[5] = TO(l32);
+        p[6] = TO(i0); p[7] = TO(i1); p[8] = TO(i2); p[9] = TO(i3);
     }
-    __device__ __forceinline__ void load(const real* p)
+    template <typename TI>
+    __device__ __forceinline__ void load(const TI* p)
     {
-        real a, b;
-        ld2(p, a, b); l10 = a; l20 = b;
-        ld2(p + 2, a, b); l21 = a; l30 = b;
-        ld2(p + 4, a, b); l31 = a; l32 = b;
-        ld2(p + 6, a, b); i0 = a; i1 = b;
-        ld2(p + 8, a, b); i2 = a; i3 = b;
+        TI a, b;
+        ld2(p, a, b); l10 = real(a); l20 = real(b);
+        ld2(p + 2, a, b); l21 = real(a); l30 = real(b);
+        ld2(p + 4, a, b); l31 = real(a); l32 = real(b);
+        ld2(p + 6, a, b); i0 = real(a); i1 = real(b);
+        ld2(p + 8, a, b); i2 = real(a); i3 = real(b);
     }
 };
 
@@ -533,7 +546,7 @@ struct WarpCtx {
                 cs[lane * 5] = (kme != real(0)) ? cs[lane * 5] + dg : real(1);
             }
             __syncwarp();
-            Chol4<real> L;
+            Chol4<double> L;               // fp32 handles too: cond(M_uu) ~ 1e3, its inverse carries the whole feedback gain
             real lg[4], lp[3][4], lj[4], lpme[4];
             real gpme = 0;                         // gradient correction of "my" position row from pinned inputs
             {
@@ -626,6 +639,8 @@ struct WarpCtx {
     }
 
     // backward sweep of the gradient only (corrector): zero offset/terminal, input gradient rt
+    // PINNED: the factors in `fac` come from a pinned round (backward_full<true>): pinned inputs take no gradient
+    template <bool PINNED = false>
     __device__ void backward_vec()
     {
         if (lane < 16) pv[lane] = 0;
@@ -636,7 +651,7 @@ struct WarpCtx {
             load_col(tile_at(N - 1 - k, k), w);
             prefetch_stage(k - 1, true);
             const real* f = facv + (size_t)k * FAC;
-            Chol4<real> L;
+            Chol4<double> L;
             L.load(f + 56);
             real lx[4] = {0, 0, 0, 0};
             if (sidx >= 0) { ld2(f + sidx * 4, lx[0], lx[1]); ld2(f + sidx * 4 + 2, lx[2], lx[3]); }
@@ -652,6 +667,10 @@ struct WarpCtx {
             real gu[4], lgc[4];
 #pragma unroll
             for (int aa = 0; aa < 4; ++aa) gu[aa] = __shfl_sync(FULL, g, aa);
+            if (PINNED) {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa) if (fx[k * 4 + aa] != real(0)) gu[aa] = 0;
+            }
             L.fsolve(gu, lgc);
             const real pold = j < 3 ? pv[j] : real(0);
             __syncwarp();
@@ -699,6 +718,101 @@ struct WarpCtx {
             }
             __syncwarp();
         }
+    }
+
+    // ---- fp32 handles only: one step of iterative refinement of the solution of the last pinned round.
+    // The fp32 Riccati recursion leaves 1e-5..1e-4 of relative error in du (cancellation in P <- M_xx - l'l).  The residual
+    // of the stationarity condition is evaluated in fp64 (state increments rolled out in double, adjoint swept back in
+    // double; the tiles themselves are fp32-rounded fp64 values, worth ~1e-6), the correction is solved with the fp32
+    // factors already in `fac` (backward_vec + forward<1>, the IPM's corrector path), and the states are re-rolled.
+    // dxd: (N+1) x 13 doubles, pvd: 16 doubles of per-warp shared memory.
+    __device__ void rollout_fp64(double* dxd, const double* dud) const
+    {
+        if (lane < NX) dxd[lane] = x0[lane] - xit[lane];
+        __syncwarp();
+        const int i = lane < NX ? lane : NX - 1;
+        for (int k = 0; k < N; ++k) {
+            const real* row = Wv + (size_t)k * WT + i * WR;
+            const double* dx = dxd + k * NX;
+            double acc = double(__ldg(row + 14)) + (i < 3 ? dx[i] : 0.0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc = fma(double(__ldg(row + c)), dud[k * 4 + c], acc);
+#pragma unroll
+            for (int s_ = 3; s_ < NX; ++s_) acc = fma(double(__ldg(row + 1 + s_)), dx[s_], acc);
+            if (lane < NX) dxd[(k + 1) * NX + lane] = acc;
+            __syncwarp();
+        }
+    }
+    // adjoint sweep in double at the inputs usol / states dxd: stationarity residual of every input into rt (fp32 storage;
+    // for a pinned input this is its multiplier).  lane j < 16 = tile column (0-3 inputs, 4-13 states 3..12).
+    __device__ void adjoint_fp64(const double* dxd, const double* dud, double* pvd)
+    {
+        if (lane < NX) pvd[lane] = double(a.QNd[lane]) * (dxd[N * NX + lane] + (xit[(size_t)N * NX + lane] - yref_e[lane]));
+        __syncwarp();
+        for (int k = N - 1; k >= 0; --k) {
+            const real* tile = Wv + (size_t)k * WT;
+            double g = 0;
+            if (lane < 14) {
+#pragma unroll
+                for (int r = 0; r < NX; ++r) g = fma(double(__ldg(tile + r * WR + lane)), pvd[r], g);
+            }
+            const double pold = lane < 3 ? pvd[lane] : 0.0;
+            const int st = lane < 3 ? lane : lane - 1;                    // state index of lanes 0-2 (positions) and 4-13
+            double pn = 0;
+            if (lane < 3 || (lane >= 4 && lane < 14))
+                pn = (lane < 3 ? pold : g) + double(a.Qd[st]) * dxd[k * NX + st] + double(__ldg(tile + st * WR + 15));
+            __syncwarp();
+            if (lane < 4) {
+                const int e = k * 4 + lane;
+                rt[e] = real(g + double(a.Rd[lane]) * dud[e] + double(rdel[e]));
+            }
+            if (lane < 3 || (lane >= 4 && lane < 14)) pvd[st] = pn;
+            __syncwarp();
+        }
+    }
+    // one refinement step, then the active set is CHECKED with the fp64 gradient of the refined point: fp32 multipliers
+    // carry ~1e-4 of relative noise, enough to mis-sign a weakly active bound (and a wrong active set is a 1e-2 error).
+    // Returns the number of inputs whose status it changed in fx (0: the active set is verified).
+    __device__ int refine_solution_fp64(double* dxd, double* pvd, real lb, real ub)
+    {
+        double* dud = pvd + 16;                      // the input increments in double: fp32 storage of du alone is worth
+        for (int e = lane; e < E; e += 32) dud[e] = double(usol[e]);      // |H| * 6e-8 |du| ~ 1e-5 of gradient noise
+        __syncwarp();
+        for (int step = 0; ; ++step) {
+            rollout_fp64(dxd, dud);
+            adjoint_fp64(dxd, dud, pvd);
+            real rmax = 0;
+            for (int e = lane; e < E; e += 32) if (fx[e] == real(0)) rmax = fmax(rmax, fabs(rt[e]));
+            rmax = warp_max(rmax);
+            if (step == 3 || (step > 0 && rmax < real(2e-7))) break;       // refined: rt holds the gradient at the final point
+            for (int e = lane; e < E; e += 32) if (fx[e] != real(0)) rt[e] = 0;
+            __syncwarp();
+            backward_vec<true>();
+            forward<1>();
+            __syncwarp();
+            for (int e = lane; e < E; e += 32) if (fx[e] == real(0)) dud[e] += double(usol[e]);
+            __syncwarp();
+        }
+        for (int e = lane; e < E; e += 32) usol[e] = real(dud[e]);
+        for (int idx = lane; idx < (N + 1) * NX; idx += 32) xtr[idx] = real(dxd[idx]);
+        int changed = 0;
+        const real gtol = real(1e-6);         // the fp32-rounded tiles themselves are worth ~1e-6 of gradient accuracy
+        for (int e = lane; e < E; e += 32) {
+            const real f = fx[e], gr = rt[e];
+            const double un = double(ubar[e]) + dud[e];
+            if (f == real(1)) { if (gr < -gtol) { fx[e] = 0; ++changed; } }
+            else if (f == real(2)) { if (gr > gtol) { fx[e] = 0; ++changed; } }
+            else if (un < double(lb) - 1e-7) { fx[e] = 1; ++changed; }
+            else if (un > double(ub) + 1e-7) { fx[e] = 2; ++changed; }
+        }
+        changed = warp_sum(changed);
+        __syncwarp();
+#ifdef QMPC_EMU_TRACE
+        if (lane == 0) { double m = 0; int np_ = 0; for (int e = 0; e < E; ++e) { if (fx[e] == real(0)) m = fmax(m, fabs((double)rt[e])); else ++np_; }
+            printf("  [trace ocp %d] fp64 check: changed %d, max |residual(free)| after refinement %.3e, pinned %d\n", ocp, changed, m, np_); }
+        __syncwarp();
+#endif
+        return changed;
     }
 
     // Primal-dual active-set rounds from the active set in fx.  Each round solves the LQR with the active inputs
@@ -783,7 +897,7 @@ struct WarpCtx {
             real u[4];
             if (MODE != 2) {
                 const real* f = facv + (size_t)k * FAC;
-                Chol4<real> L;
+                Chol4<double> L;
                 L.load(f + 56);
                 const real xo = j < 3 ? xp[j] : (j < NX ? wv[j + 1] : real(0));
                 real v[4] = {0, 0, 0, 0};
@@ -1017,7 +1131,7 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
                 for (int e = lane; e < E; e += 32)
                     c.rt[e] = -(smu - so * c.cl[e]) / c.tl[e] + (smu - so * c.cu[e]) / c.tu[e];
                 __syncwarp();
-                c.backward_vec();
+                c.template backward_vec<false>();
                 c.template forward<1>();
                 __syncwarp();
                 real apx = real(1e30), adx = real(1e30);
@@ -1064,6 +1178,32 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
         if (lane == 0) { a.cost[ocp] = nan(""); a.status[ocp] = status; a.iters[ocp] = it; a.rounds[ocp] = rounds; }
         if (a.timeline && lane == 0) a.timeline[2 * ocp + 1] = global_ns();
         return;
+    }
+    if (sizeof(real) == 4 && a.refine_off > 0 && (exact || status == QMPC_STATUS_OK_)) {
+        // fp32 handles: refine the fp32 solution with an fp64 residual and VERIFY its active set with the fp64 gradient.
+        // Where the check moves the active set (or the fp32 rounds never settled and the IPM point is all there is), the
+        // rounds continue here with the fp64 check as their update rule: pinned solve in fp32, refinement, check.
+        double* dxd = reinterpret_cast<double*>(sm + a.refine_off);
+        if (!exact) {
+            for (int e = lane; e < E; e += 32) c.fx[e] = c.tl[e] < c.ll[e] ? real(1) : (c.tu[e] < c.lu[e] ? real(2) : real(0));
+        }
+        bool solved = exact;                 // usol / fac hold the pinned solve of the active set in fx
+        exact = false;
+        for (int pass = 0; pass < 10 && !exact; ++pass) {
+            if (!solved) {
+                for (int e = lane; e < E; e += 32)
+                    c.fv[e] = c.fx[e] == real(1) ? lb - c.ubar[e] : (c.fx[e] == real(2) ? ub - c.ubar[e] : real(0));
+                __syncwarp();
+                c.template backward_full<true>();
+                c.template forward<0, true>();
+                __syncwarp();
+                ++rounds;
+            }
+            exact = c.refine_solution_fp64(dxd, dxd + (N + 1) * NX, lb, ub) == 0;
+            solved = false;
+        }
+        if (!exact) { exact = true; status = QMPC_STATUS_MAXITER_; }      // unverified: the last refined point is returned, flagged
+        else status = QMPC_STATUS_OK_;
     }
     // ---- 3. full step: new iterate = solution of the QP, states re-rolled through the linearised dynamics
     for (int e = lane; e < E; e += 32) {

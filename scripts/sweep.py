@@ -21,7 +21,7 @@ from mpc_quad_ros_b200.trajectory import lemniscate_trajectories, random_smooth_
 from oracle import oracle as orc
 from helpers import make_gp, oracle_solve_batch, random_ocp_batch, u_rel, x_rel
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 W, K = 10, 40
 
 

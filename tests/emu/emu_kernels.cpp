@@ -15,11 +15,13 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
 {
     const int B = o->batch, N = o->n_nodes;
     std::vector<real> W(((size_t)B * N + 1) * WT), fac((size_t)B * N * FAC);
-    LinArgs<real> la;
+    LinArgs<double, real> la;
     fill_lin_args(*o, la);
     la.xit = xit; la.uit = uit; la.yref = yref; la.alpha = alpha; la.gpX = o->gp_X; la.W = W.data();
     const unsigned threads = 128, total = (unsigned)B * N * 16;
-    emu::launch((total + threads - 1) / threads, threads, 0, [&]() { qmpc_linearize_kernel<real>(la); });
+    emu::launch((total + threads - 1) / threads, threads, 0, [&]() { qmpc_linearize_kernel<double, real>(la); });
+    if (getenv("EMU_ROUND_TILES_FP32"))      // experiment: how much of the fp32 build's error is the rounding of the tile data alone
+        for (auto& v : W) v = real(float(v));
     IpmArgs<real> ia;
     fill_ipm_args(*o, ia);
     ia.x0 = x0; ia.yref = yref; ia.yref_e = yref_e; ia.xit = xit; ia.uit = uit; ia.W = W.data(); ia.fac = fac.data();

@@ -293,19 +293,27 @@ def test_simulate_trajectory_single_vehicle_reference_api():
     assert rel_err(np.stack(log["rgp_mu_g_t"][-1]), ref.mu[0]) < 1e-7
 
 
-def test_fp32_solver_runs_and_is_close():
-    """fp32 Riccati/IPM build: finite, feasible, and close to the oracle on non-degenerate problems.  The 1e-4 bar of
-    north_star needs the active-set polish that is not in the fp32 path yet (DESIGN.md, fp32 status) -> reported, loose."""
-    B, N, M = 48, 20, 20
-    dt = 1.0 / N
+TOL_F32 = 1e-4      # north_star: controls and predicted trajectories within 1e-4 relative in the fp32 build
+
+
+@pytest.mark.parametrize("N,M,seed,amps", [(20, 20, 11, (2.0,)), (20, 20, 140, (2.0, 8.0, 25.0)), (10, 0, 110, (2.0, 8.0, 25.0)),
+                                           (50, 20, 170, (2.0, 8.0, 25.0)), (10, 50, 157, (2.0, 8.0)), (20, 100, 220, (2.0, 8.0, 25.0))])
+def test_fp32_solver_within_1e4_of_oracle(N, M, seed, amps):
+    """fp32 build (qmpc_config.precision = 32): the linearisation runs in fp64 and is rounded once into fp32 stage tiles, the
+    Riccati / IPM / active-set solver runs in fp32 and its result takes one step of iterative refinement with an fp64
+    residual (mpc_kernels.cuh refine_solution_fp64).  Tolerance of north_star for fp32: 1e-4 relative, also with the thrust
+    limits active (amplitudes 8 and 25 saturate the inputs)."""
+    B, dt = 48, 1.0 / N
     quad = orc.quad_hummingbird()
-    gp = make_gp(M)
-    sc = random_ocp_batch(B, N, dt, quad, gp, seed=11, amp_choices=(2.0,))
+    gp = make_gp(M) if M else None
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=seed, amp_choices=amps)
     x, u, cost, st, it = _solve_batch(sc, B, N, gp, precision=32)
     xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
     assert np.isfinite(u).all() and ((u >= 0) & (u <= 1)).all()
-    print(f"fp32: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} status={np.bincount(st)}")
-    assert u_rel(u, uo) < 5e-2
+    print(f"fp32 N={N} M={M}: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} status={np.bincount(st)}")
+    ok = st == 0
+    assert ok.mean() >= 0.95
+    assert u_rel(u[ok], uo[ok]) < TOL_F32 and x_rel(x[ok], xo[ok]) < TOL_F32
 
 
 @pytest.mark.parametrize("M", [20, 50])

@@ -47,8 +47,10 @@ def test_emulated_solve_fp32_within_1e4(variant):
     xe, ue = sc["xit"].copy(), sc["uit"].copy()
     r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], None, xe, ue, f32=True, variant=variant)
     xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, None)
-    assert (r["status"] != 2).all()
-    assert u_rel(ue, uo) < 2e-2     # fp32 IPM without active-set polish: logic check only (see DESIGN.md, fp32 status)
+    assert (r["status"] == 0).all()
+    # fp32 build: fp64 linearisation rounded to fp32 tiles, fp32 Riccati/IPM/active-set rounds, one step of iterative
+    # refinement with an fp64 residual -> north_star's fp32 tolerance (1e-4 relative) with a wide margin
+    assert u_rel(ue, uo) < 1e-4 and x_rel(xe, xo) < 1e-4, (u_rel(ue, uo), x_rel(xe, xo))
 
 
 @VARIANTS
