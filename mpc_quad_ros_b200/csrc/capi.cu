@@ -726,6 +726,8 @@ int qmpc_closed_loop_step(qmpc_handle_t h, qrgp_handle_t g, const double* traj, 
 
 // ------------------------------------------------------------------------------------------- RGP* learning
 
+int qrgpl_destroy(qrgpl_handle_t g);
+
 int qrgpl_create(int n_models, int n_basis, const double* X, const double* theta, int device, qrgpl_handle_t* out)
 {
     if (!X || !theta || !out) return fail(QMPC_ERR_ARG, "null argument");
@@ -755,7 +757,8 @@ int qrgpl_create(int n_models, int n_basis, const double* X, const double* theta
     }
     std::vector<double> Kxi(M * M);
     for (size_t i = 0; i < M; ++i) for (size_t j = 0; j < M; ++j) Kxi[i * M + j] = W[i * 2 * M + M + j];
-    qrgpl_model* g = new qrgpl_model();
+    std::unique_ptr<qrgpl_model, int (*)(qrgpl_handle_t)> guard(new qrgpl_model(), qrgpl_destroy);     // released on every early return
+    qrgpl_model* g = guard.get();
     g->n = n_models; g->M = n_basis; g->device = device;
 #define ALLOC(p, nb) CU_TRY(cudaMalloc(reinterpret_cast<void**>(&(p)), (nb)))
     ALLOC(g->X, M * 8); ALLOC(g->mu_g, n * M * 8); ALLOC(g->C_g, n * M * M * 8); ALLOC(g->mu_eta, n * 3 * 8);
@@ -776,7 +779,7 @@ int qrgpl_create(int n_models, int n_basis, const double* X, const double* theta
     const int smem = rgp_learn_smem_doubles(n_basis) * 8;
     CU_TRY(cudaFuncSetAttribute(qrgp_learn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU_TRY(cudaDeviceSynchronize());
-    *out = g;
+    *out = guard.release();
     return QMPC_OK;
 }
 
@@ -904,23 +907,24 @@ int qmpc_fma_peak(int precision, double* tflops, void* stream)
     CU_TRY(cudaGetDevice(&dev));
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int blocks = sms * 8, threads = 256, iters = 4096;
-    double* sink = nullptr;
-    CU_TRY(cudaMalloc(&sink, 8));
-    cudaEvent_t e0, e1;
-    CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+    struct Scratch {            // released on every return path
+        double* sink = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Scratch() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (sink) cudaFree(sink); }
+    } sc;
+    CU_TRY(cudaMalloc(&sc.sink, 8));
+    CU_TRY(cudaEventCreate(&sc.e0)); CU_TRY(cudaEventCreate(&sc.e1));
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
-        CU_TRY(cudaEventRecord(e0, S(stream)));
-        if (precision == 64) fma_peak_kernel<double><<<blocks, threads, 0, S(stream)>>>(iters, sink);
-        else fma_peak_kernel<float><<<blocks, threads, 0, S(stream)>>>(iters, sink);
+        CU_TRY(cudaEventRecord(sc.e0, S(stream)));
+        if (precision == 64) fma_peak_kernel<double><<<blocks, threads, 0, S(stream)>>>(iters, sc.sink);
+        else fma_peak_kernel<float><<<blocks, threads, 0, S(stream)>>>(iters, sc.sink);
         LAUNCH_CHECK();
-        CU_TRY(cudaEventRecord(e1, S(stream)));
-        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventRecord(sc.e1, S(stream)));
+        CU_TRY(cudaEventSynchronize(sc.e1));
         float ms = 0;
-        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        CU_TRY(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
         if (rep > 0 && ms < best) best = ms;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     *tflops = 2.0 * 16.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
     return QMPC_OK;
 }

@@ -1,0 +1,86 @@
+"""Turn the gpurun_out/ captures of scripts/gpu_final.sh into the tracked round-2 summaries under profiles/.
+usage (CPU box, after the gpurun call): python scripts/make_profiles_r02.py"""
+import collections, csv, json, os, shutil, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = "r02"
+
+
+def short(name):
+    return name.split("(")[0].replace("qmpc::", "").replace("void ", "")
+
+
+# ---- ncu launch list of the bench command -> shares
+path = os.path.join(G, f"{tag}_launches_bench.csv")
+if os.path.exists(path):
+    rows = list(csv.reader(open(path)))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, data = r, rows[i + 1:]
+            break
+    kn, mv, mn = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    agg = collections.OrderedDict()
+    for r in data:
+        if len(r) > mv and r[mn] == "gpu__time_duration.sum":
+            agg.setdefault(short(r[kn]), []).append(float(r[mv].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    own = {k: v for k, v in agg.items() if not k.startswith("at::")}
+    with open(os.path.join(P, f"{tag}_launch_shares_bench.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e\n"
+                "  --no-extra-legs --latency-steps 20   (the benchmark command: value leg on 8 streams, roofline leg, latency leg; the cold first\n"
+                "step of every leg included).  Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n")
+        for k, v in own.items():
+            f.write(f"{k:58s} n={len(v):4d} mean={sum(v) / len(v) / 1000:9.1f} us  share={100 * sum(v) / tot:5.1f}%\n")
+        f.write(f"{'torch element-wise / copy / reduce kernels (setup, statistics)':58s} n={sum(len(v) for k, v in agg.items() if k.startswith('at::')):4d} "
+                f"share={100 * sum(sum(v) for k, v in agg.items() if k.startswith('at::')) / tot:5.1f}%\n")
+    shutil.copy(path, os.path.join(P, f"{tag}_launches_bench_ncu.csv"))
+    print(open(os.path.join(P, f"{tag}_launch_shares_bench.txt")).read())
+
+# ---- ncu --set full summaries
+with open(os.path.join(P, f"{tag}_solver_summary.txt"), "w") as f:
+    f.write("ncu --set full --clock-control none --import-source on -k 'regex:qmpc_ipm|qmpc_dense|qmpc_linearize' of scripts/profile_step.py\n"
+            "(B=4096, N=20, M=20, fp64, single stream).  step 12 = start-up transient (busy step: the screening launch keeps contracting OCPs\n"
+            "for up to 8 rounds), step 60 = steady state.  dram bytes below are what bench.py quotes as roofline.traffic (step 60, screening + dense).\n")
+    for step in (12, 60):
+        rep = os.path.join(G, f"{tag}_prof_step{step}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        for title, rx in (("K1 qmpc_linearize_kernel", "qmpc_linearize"), ("K2a qmpc_ipm_kernel (screening launch)", "qmpc_ipm"), ("K2b qmpc_dense_kernel", "qmpc_dense")):
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, rx], capture_output=True, text=True).stdout
+            f.write(f"\n=== step {step}: {title}\n{out}")
+print(open(os.path.join(P, f"{tag}_solver_summary.txt")).read()[:3000])
+
+# ---- plain copies
+for src, dst in ((f"{tag}_bench_N1.json", f"{tag}_bench_N1.json"), (f"{tag}_bench_N1_steady.json", f"{tag}_bench_N1_steady_100steps.json"),
+                 (f"{tag}_bench_ref.json", f"{tag}_bench_reference_arm.json"), (f"{tag}_timeline_step8.txt", f"{tag}_timeline_step8_busy.txt"),
+                 (f"{tag}_timeline_step60.txt", f"{tag}_timeline_step60_steady.txt"), (f"{tag}_transient.txt", f"{tag}_transient.txt"),
+                 (f"{tag}_pytest_gpu.log", f"{tag}_pytest_gpu.log"), (f"{tag}_smoke.log", f"{tag}_smoke.log")):
+    if os.path.exists(os.path.join(G, src)):
+        shutil.copy(os.path.join(G, src), os.path.join(P, dst))
+with open(os.path.join(P, f"{tag}_sanitizer.txt"), "w") as f:
+    f.write("compute-sanitizer on the round-2 kernels, odd batch B=67 (partial warps / CTAs), a few closed-loop steps from the cold start\n"
+            "(scripts/profile_step.py: K1, screening, dense incl. TMA bulk copies + mbarriers, RGP regress, plant; PREC=32: the fp32 Riccati\n"
+            "kernel with its fp64 refinement) and the RGP / shared-swarm / reference-generator kernels through their GPU tests.\n")
+    for name in ("memcheck_fp64", "racecheck_fp64", "memcheck_fp32", "racecheck_fp32", "racecheck_rgp"):
+        pth = os.path.join(G, f"{tag}_{name}.txt")
+        if os.path.exists(pth):
+            lines = [l for l in open(pth).read().splitlines() if l.startswith("=========") or "passed" in l or "status counts" in l]
+            f.write(f"\n--- {name}\n" + "\n".join(lines[-6:]) + "\n")
+print(open(os.path.join(P, f"{tag}_sanitizer.txt")).read())
+
+# ---- SASS evidence of the TMA bulk copies
+so = os.path.join(ROOT, "mpc_quad_ros_b200", "csrc", "libqmpc.so")
+sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+cur, hits = None, collections.OrderedDict()
+for line in sass.splitlines():
+    if "Function :" in line:
+        cur = line.split("Function :")[1].strip()
+    elif any(t in line for t in ("UBLKCP", "SYNCS.", "UTMA")):
+        hits.setdefault(cur, []).append(line.strip()[:110])
+with open(os.path.join(P, f"{tag}_sass_tma.txt"), "w") as f:
+    f.write("cuobjdump -sass mpc_quad_ros_b200/csrc/libqmpc.so | grep -E 'UBLKCP|SYNCS|UTMA'   (cp.async.bulk = UBLKCP.S.G, mbarrier = SYNCS.*)\n")
+    for fn, ls in hits.items():
+        f.write(f"\n{fn}\n")
+        for l in ls:
+            f.write("    " + l + "\n")
+print(open(os.path.join(P, f"{tag}_sass_tma.txt")).read()[:1500])
