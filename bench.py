@@ -21,6 +21,7 @@ Legs of one run (all in the same JSON line; every key says which leg it belongs 
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -340,10 +341,15 @@ def b200_arm(a):
         return make_loop_generic(count, traj_np[first:first + count], x0_np[first:first + count], spec, shared=a.shared_rgp)
 
     def barrier():
+        # handles of finished legs are released here, never inside a timed region (their destructors call cudaFree,
+        # which synchronises the device); the collector stays off while a region is timed
+        gc.collect()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    gc.disable()
 
     # ---------------- value: everything resident, K timed steps
     if B % max(a.groups, 1) != 0:
@@ -382,6 +388,7 @@ def b200_arm(a):
     loop2 = make_loop()
     for _ in range(a.warmup):
         loop2.step()
+    gc.collect()
     torch.cuda.synchronize()
     _capi.check(lib.qmpc_timing_enable(loop2.opt._h, 1))
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -407,6 +414,7 @@ def b200_arm(a):
     loopL = make_loop_generic(B, None, x0_l, (kind_l, par_l, K_lat), shared=a.shared_rgp)
     for _ in range(a.warmup):
         loopL.step()
+    gc.collect()
     torch.cuda.synchronize()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_lat + 1)]
     evs[0].record()

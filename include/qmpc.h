@@ -74,7 +74,7 @@ typedef struct {
     int bail_round;        /* round (0-based) from which a non-contracting change count ends a warm attempt: 0 -> 2 */
     int bail_changed;      /* a warm round that still moves more inputs than this ends the attempt: 0 -> never */
     int final_rollout;     /* >0 -> always re-roll the horizon at the end of a solve (A/B knob): 0 -> reuse the last sweep */
-    int dense_grid;        /* persistent CTAs of the dense launch: 0 -> min(resident CTAs, max(32, B/6)) */
+    int dense_grid;        /* persistent CTAs of the dense launch: 0 -> min(resident CTAs, max(32, B/3)) */
     int screen_rounds_busy; /* round limit of the screening launch in a BUSY step: 0 -> 8, <0 -> same as screen_rounds.  A step
                               is busy when the previous step left more than screen_busy_pct % of the vehicles unsettled
                               after screen_rounds rounds (start-up transients, aggressive references): the dense launch

@@ -162,9 +162,10 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
         int per_sm = 0, sms = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qmpc_dense_kernel<double>, DN_THREADS, smemd));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        // persistent CTAs looping over the hard list: about 5 % of the vehicles are on it in steady state, so a sixth of
-        // the batch (at most one resident wave) covers it without queueing empty CTAs behind other streams' kernels
-        const size_t want = cfg->dense_grid > 0 ? (size_t)cfg->dense_grid : std::max<size_t>(32, B / 6);
+        // persistent CTAs taking items of the hard list from a work queue: 10-15 % of the vehicles are on it in steady
+        // state and up to 40 % in a start-up transient; a third of the batch (at most one resident wave) measured best
+        // (profiles/r02_policy_ab.txt), more only queues empty CTAs behind other streams' kernels
+        const size_t want = cfg->dense_grid > 0 ? (size_t)cfg->dense_grid : std::max<size_t>(32, B / 3);
         h->dense_grid = (int)std::min<size_t>(std::min<size_t>(B, want), (size_t)std::max(1, per_sm) * sms);
     }
     CU_TRY(cudaDeviceSynchronize());

@@ -29,8 +29,8 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
 
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }
 // per-warp shared memory of the Riccati kernel (reals): working set, then (fp64 QMPC_RING builds) the tile ring and one
-// 8-byte mbarrier per slot.  `full`: the IPM layout (13 vectors); otherwise the screening layout (7 vectors).
-inline int ipm_ring_off(int N, bool full) { return (SM_VEC + (full ? SM_NVEC : 7) * 4 * N + (N + 1) * 13 + 9) & ~1; }
+// 8-byte mbarrier per slot.  `full`: the IPM layout (13 vectors); otherwise the screening layout (6 vectors).
+inline int ipm_ring_off(int N, bool full) { return (SM_VEC + (full ? SM_NVEC : 6) * 4 * N + (N + 1) * 13 + 9) & ~1; }
 inline int ipm_smem_reals(int N, bool full, bool fp64)
 {
     const int ring = fp64 ? QMPC_RING : 0;

@@ -976,10 +976,11 @@ __global__ void __launch_bounds__(WARPS * 32, QMPC_IPM_MIN_WARPS / WARPS) qmpc_i
     c.Ls = sm + SM_LS; c.cs = sm + SM_CS;
     real* v = sm + SM_VEC;
     if (a.hard_count) {
-        // screening mode never enters the IPM: only the 7 vectors of the active-set rounds are laid out (9.5 KB per OCP
-        // instead of 13.5 KB leaves ~100 KB of the SM's L1 for the stage tiles)
-        c.usol = v; c.ua = v + E; c.ucur = v + 2 * E; c.ubar = v + 3 * E; c.rdel = v + 4 * E; c.cl = v + 5 * E; c.cu = v + 6 * E;
-        c.xtr = v + 7 * E;
+        // screening mode never enters the IPM: only the 6 vectors of the active-set rounds are laid out (the new inputs
+        // of the epilogue reuse the multiplier vector, which is dead by then): 12.8 KB per OCP with the tile ring,
+        // 16 warps per SM
+        c.usol = v; c.ua = v + E; c.ucur = v + E; c.ubar = v + 2 * E; c.rdel = v + 3 * E; c.cl = v + 4 * E; c.cu = v + 5 * E;
+        c.xtr = v + 6 * E;
         c.rt = c.dR = c.ll = c.lu = c.tl = c.tu = v;
     } else {
         c.rt = v; c.dR = v + E; c.usol = v + 2 * E; c.ua = v + 3 * E; c.ucur = v + 4 * E; c.ll = v + 5 * E;

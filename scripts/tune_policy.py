@@ -2,7 +2,7 @@
 For every policy string: `reps` fresh closed loops; each reports steps/s in the driver's window (steps 5..25 from the zero
 iterate) and in a steady window (steps 40..100).  usage: python scripts/tune_policy.py [reps] "opts1" "opts2" ...
 (opts like screen_rounds=5,bail_round=3; "" = library defaults)"""
-import os, sys
+import gc, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -30,6 +30,7 @@ def run(opts):
         return ClosedLoop(quad, opt, torch.as_tensor(traj[first:first + count]), torch.as_tensor(x0[first:first + count]))
 
     loop = GroupedClosedLoop(make, B, G) if G > 1 else make()
+    gc.collect(); gc.disable()          # the previous run's handles are freed (cudaFree synchronises) before anything is timed
     out = []
     done = 0
     for (upto, timed) in ((5, False), (25, True), (40, False), (100, True)):
@@ -43,6 +44,7 @@ def run(opts):
         torch.cuda.synchronize()
         if timed: out.append(B * (upto - done) / (e0.elapsed_time(e1) * 1e-3))
         done = upto
+    gc.enable()
     return out
 
 
