@@ -69,7 +69,10 @@ inline void fill_ipm_args(const qmpc_config& c, IpmArgs<real>& a)
     // initial multipliers of a cold IPM: clip(0.02 * mean|dJ/du(box centre)|, 0.1, 1e5).  The upper clip used to be 100: a vehicle
     // 30-80 m off its reference (gradients of 1e3-1e4, 75 of 80 inputs saturated) then spent 25-45 iterations growing the
     // multipliers, 8-15 now; ordinary problems are unaffected (profiles/r02_lam0_sweep.txt)
-    a.lam0_scale = real(0.02); a.lam0_min = real(0.1); a.lam0_max = real(1e5);
+#ifndef QMPC_LAM0_SCALE
+#define QMPC_LAM0_SCALE 0.02
+#endif
+    a.lam0_scale = real(QMPC_LAM0_SCALE); a.lam0_min = real(0.1); a.lam0_max = real(1e5);
 #ifdef QMPC_EMU       // tuning hook of the test-only emulation build (scripts/replay_hard.py)
     if (getenv("EMU_LAM0_SCALE")) a.lam0_scale = real(atof(getenv("EMU_LAM0_SCALE")));
     if (getenv("EMU_LAM0_MAX")) a.lam0_max = real(atof(getenv("EMU_LAM0_MAX")));

@@ -844,6 +844,9 @@ struct WarpCtx {
             ++rounds;
             int changed = 0;
             unsigned long long fp = 0;
+#ifdef QMPC_EMU_TRACE
+            int tr_kmax = -1;
+#endif
             for (int e = lane; e < E; e += 32) {
                 const real f = fx[e], un = ubar[e] + usol[e], gr = grad[e];
                 if (f == real(1)) { if (gr < -a.refine_gtol) { fx[e] = 0; ++changed; } }
@@ -851,9 +854,22 @@ struct WarpCtx {
                 else if (un < lb) { fx[e] = 1; ++changed; }
                 else if (un > ub) { fx[e] = 2; ++changed; }
                 fp += active_set_term(e, fx[e]);
+#ifdef QMPC_EMU_TRACE
+                if (fx[e] != f) tr_kmax = (e >> 2) > tr_kmax ? (e >> 2) : tr_kmax;
+#endif
             }
+#ifdef QMPC_EMU_TRACE
+            tr_kmax = warp_max(tr_kmax);
+#endif
             changed = warp_sum(changed);
             fp = warp_sum(fp);
+#ifdef QMPC_EMU_TRACE
+            if (lane == 0) {
+                int kmax = -1, kmin = 1 << 20, np_ = 0;
+                for (int e = 0; e < E; ++e) { if (fx[e] != real(0)) ++np_; }
+                printf("  [trace ocp %d] riccati round %d: changed %d pinned %d kmax %d\n", ocp, round + 1, changed, np_, tr_kmax);
+            }
+#endif
             if (!changed) return true;
             const bool cycling = hist.seen_then_push(fp, lane);   // the deterministic iteration met this active set before: it cycles
             if ((round + 1 == mark_round || (cycling && round + 1 < mark_round)) && mark_counter && lane == 0) atomicAdd(mark_counter, 1);

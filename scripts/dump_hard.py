@@ -12,6 +12,7 @@ from mpc_quad_ros_b200.trajectory import random_smooth_trajectories
 B, N, M = 4096, 20, 20
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 it_min, rd_min = int(os.environ.get("IT_MIN", 14)), int(os.environ.get("RD_MIN", 20))
+sample_step, sample_n = int(os.environ.get("SAMPLE_STEP", -1)), int(os.environ.get("SAMPLE_N", 64))   # also dump a random sample of one step
 quad = Quadrotor3D(drag=True, batch=B).set_hummingbird_params()
 gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=[3.0, 0.1, 0.01], batch=B)
 opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe)
@@ -25,8 +26,10 @@ for s in range(steps):
     if s >= 1:
         hist_it += np.bincount(it.cpu().numpy().clip(0, 63), minlength=64); hist_rd += np.bincount(rd.cpu().numpy().clip(0, 63), minlength=64)
         sel = torch.nonzero((it >= it_min) | (rd >= rd_min)).flatten().tolist()
-        for b in sel[:6]:
-            if len(cases) < 60:
+        if s == sample_step:
+            sel = np.random.default_rng(0).choice(B, sample_n, replace=False).tolist()
+        for b in (sel if s == sample_step else sel[:6]):
+            if len(cases) < 60 or s == sample_step:
                 cases.append(dict(step=s, b=b, x0=x_now[b].cpu().numpy(), chunk=loop.chunk[b].cpu().numpy(), alpha=alpha[b].cpu().numpy(),
                                   xit=xit[b].cpu().numpy(), uit=uit[b].cpu().numpy(), act=act[b].cpu().numpy(),
                                   status=int(st[b]), iters=int(it[b]), rounds=int(rd[b])))

@@ -49,10 +49,13 @@ def _solve_batch(sc, B, N, gp, precision=64, quad_name="hummingbird", mu_tol=0.0
     return x_opt.cpu().numpy(), w_opt.cpu().numpy(), cost.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
 
 
-@pytest.mark.parametrize("N,M,seed", [(20, 20, 140), (10, 0, 110), (50, 20, 170), (7, 50, 157), (20, 100, 220), (50, 20, 1070), (20, 50, 1070)])
+@pytest.mark.parametrize("N,M,seed", [(20, 20, 140), (10, 0, 110), (50, 20, 170), (7, 50, 157), (20, 100, 220), (50, 20, 1070), (20, 50, 1070),
+                                      (1, 0, 1), (2, 3, 2), (3, 20, 3), (21, 20, 21)])
 def test_solve_fp64_vs_oracle(N, M, seed):
     """(50, 20, 1070) and (20, 50, 1070) are the cells of profiles/r01_sweep.md where an early exit of the post-IPM
-    active-set rounds once left an IPM-accurate (3.5e-6) instead of an exact answer"""
+    active-set rounds once left an IPM-accurate (3.5e-6) instead of an exact answer; N = 1, 2, 3 are horizons shorter than
+    or equal to the tile ring / condensing chunk (TMA ring and mbarrier phases at their edges), N = 21 the largest horizon
+    of the dense kernel"""
     B, dt = 48, 1.0 / N
     quad = orc.quad_hummingbird()
     gp = make_gp(M) if M else None
@@ -69,7 +72,7 @@ def test_solve_fp64_vs_oracle(N, M, seed):
     assert ((u > 0 - 1e-12) & (u < 1 + 1e-12)).all()
     assert np.abs(x[:, 0] - sc["x0"]).max() == 0.0
     nact = ((uo < 1e-9) | (uo > 1 - 1e-9)).sum()
-    assert nact > 0                                    # the batch does exercise active thrust limits
+    assert nact > 0 or N < 3                           # the batch does exercise active thrust limits
     print(f"N={N} M={M}: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} ipm iters mean={it.mean():.1f} (oracle {ito.mean():.1f})")
 
 
