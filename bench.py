@@ -555,9 +555,9 @@ def b200_arm(a):
         for i in range(a.warmup, a.warmup + a.steps):
             e2e_step(i)
         e2e_drain()                                                 # every u0 of the last step is on the host
+        wall = (time.perf_counter() - t0) * 1e3                     # host clock: ends when the host holds the last control
         g1.record()
         barrier()
-        wall = (time.perf_counter() - t0) * 1e3
         te = torch.tensor([max(g0.elapsed_time(g1), wall)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
