@@ -543,8 +543,21 @@ static int regress_launch(qrgp_model* g, const double* xt, const double* yt, voi
     RgpArgs a;
     a.B = g->B; a.M = g->M; a.X = g->X; a.theta = g->theta; a.Kx_inv = g->Kx_inv; a.mu = g->mu; a.C = g->C;
     a.alpha = g->alpha; a.xt = xt; a.yt = yt;
-    const size_t smem = (size_t)RGP_WARPS * 3 * g->M * 8;
-    qrgp_regress_kernel<RGP_WARPS><<<cdiv((long long)g->B * 3, RGP_WARPS), RGP_WARPS * 32, smem, S(stream)>>>(a);
+    if (g->M % 2 == 0 && g->M <= RGP_TMA_MAXM) {
+        // covariance staged through shared memory by TMA bulk copies; fewer warps per block as the per-model block grows
+        const size_t per_warp = (size_t)rgp_tma_reals(g->M) * 8;
+        const long long models = (long long)g->B * 3;
+        if (per_warp * 8 <= 48 * 1024) {
+            qrgp_regress_tma_kernel<8><<<cdiv(models, 8), 8 * 32, per_warp * 8, S(stream)>>>(a);
+        } else if (per_warp * 2 <= 48 * 1024) {
+            qrgp_regress_tma_kernel<2><<<cdiv(models, 2), 2 * 32, per_warp * 2, S(stream)>>>(a);
+        } else {
+            qrgp_regress_tma_kernel<1><<<models, 32, per_warp, S(stream)>>>(a);
+        }
+    } else {
+        const size_t smem = (size_t)RGP_WARPS * 3 * g->M * 8;
+        qrgp_regress_kernel<RGP_WARPS><<<cdiv((long long)g->B * 3, RGP_WARPS), RGP_WARPS * 32, smem, S(stream)>>>(a);
+    }
     LAUNCH_CHECK();
     g->pushed = true;
     return QMPC_OK;

@@ -79,6 +79,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// shared -> global counterpart (bulk async-group completion): the issuing thread commits and, before the buffer is reused or
+// the kernel ends, waits until the source has been read.  Writers of the buffer run fence_proxy_async() first.
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_s2g_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
     asm volatile(
@@ -96,6 +104,8 @@ __device__ __forceinline__ void mbar_init(unsigned long long*, int) {}
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void mbar_expect(unsigned long long*, unsigned) {}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulk_s2g_wait_read() {}
 __device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
 #endif
 // consumers' side: every thread of the CTA (resp. lane of the warp) calls this after the issuing thread has issued

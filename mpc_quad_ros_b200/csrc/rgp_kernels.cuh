@@ -107,6 +107,91 @@ __global__ void __launch_bounds__(WARPS * 32) qrgp_regress_kernel(RgpArgs a)
     }
 }
 
+// The same update with the covariance staged through shared memory by TMA bulk copies (M even, M <= RGP_TMA_MAXM): lane 0
+// starts one cp.async.bulk of the model's C (8 M^2 bytes, contiguous) onto an mbarrier, the warp computes kv / Jt meanwhile,
+// forms w = Jt C (lane = column) and cj = C Jt^T (lane = row) from shared memory without a single shuffle, applies the
+// rank-1 update in place and sends C back with one bulk store while mu and alpha are finished.  C crosses HBM exactly once
+// in each direction (16 M^2 bytes per model, the algorithmic figure) and all 32 lanes take part in the element-wise pass.
+// dynamic smem per warp: M*M + 4*M + 2 doubles (C, kv, Jt, cj, w, mbarrier)
+constexpr int RGP_TMA_MAXM = 64;
+__host__ __device__ constexpr int rgp_tma_reals(int M) { return M * M + 4 * M + 2; }
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) qrgp_regress_tma_kernel(RgpArgs a)
+{
+    QMPC_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int model = blockIdx.x * WARPS + warp;           // (vehicle, axis)
+    if (model >= a.B * 3) return;
+    const int M = a.M, MM = M * M, d = model % 3;
+    double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * rgp_tma_reals(M);
+    double *Cs = sm, *kv = sm + MM, *Jt = kv + M, *cj = Jt + M, *wv = cj + M;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(wv + M);
+    const double L = a.theta[3 * d], sf = a.theta[3 * d + 1], sn = a.theta[3 * d + 2];
+    const double iL2 = 1.0 / (L * L), sf2 = sf * sf;
+    const double* X = a.X + d * M;
+    const double* Ki = a.Kx_inv + (size_t)d * M * M;
+    double* mu = a.mu + (size_t)model * M;
+    double* Cm = a.C + (size_t)model * MM;
+    const double xt = a.xt[model], yt = a.yt[model];
+    if (!(xt - xt == 0.0) || !(yt - yt == 0.0)) return;    // non-finite sample = "no update for this axis"
+    const unsigned bytes = (unsigned)(MM * sizeof(double));
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect(bar, bytes);
+        bulk_g2s(Cs, Cm, bytes, bar);
+    }
+    for (int i = lane; i < M; i += 32) kv[i] = rbf_k(xt, X[i], iL2, sf2);
+    __syncwarp();
+    double mp = 0, jk = 0;
+    for (int j = lane; j < M; j += 32) {
+        double s = 0;
+        for (int i = 0; i < M; ++i) s += kv[i] * __ldg(Ki + (size_t)i * M + j);
+        Jt[j] = s;
+        mp += s * mu[j];
+        jk += s * kv[j];
+    }
+    mp = warp_sum(mp); jk = warp_sum(jk);
+    __syncwarp();
+    bulk_wait_warp(bar, 0);
+    double jcj = 0;
+    for (int j = lane; j < M; j += 32) {
+        double w = 0, c = 0;
+        for (int i = 0; i < M; ++i) w += Jt[i] * Cs[i * M + j];             // w_j  = (Jt C)_j     : row reads, conflict-free
+        for (int i = 0; i < M; ++i) c += Cs[j * M + i] * Jt[i];             // cj_j = (C Jt^T)_j   : lane j walks its own row
+        wv[j] = w; cj[j] = c;
+        jcj += w * Jt[j];
+    }
+    jcj = warp_sum(jcj);
+    __syncwarp();
+    const double b = rbf_k(xt, xt, iL2, sf2) - jk;
+    const double sinv = 1.0 / (b + jcj + sn * sn);
+    const double innov = yt - mp;
+    {   // C -= (cj / s) w, every lane 1/32 of the elements; (i, j) of element e = lane + 32 t advance without a division
+        int i = lane / M, j = lane - i * M;
+        const int di = 32 / M, dj = 32 - di * M;
+        for (int e = lane; e < MM; e += 32) {
+            Cs[e] -= cj[i] * sinv * wv[j];
+            i += di; j += dj;
+            if (j >= M) { j -= M; ++i; }
+        }
+    }
+    fence_proxy_async();                                   // this lane's writes to Cs, before the async proxy reads them
+    __syncwarp();
+    if (lane == 0) bulk_s2g(Cm, Cs, bytes);
+    for (int i = lane; i < M; i += 32) { const double v = mu[i] + cj[i] * sinv * innov; mu[i] = v; kv[i] = v; }
+    __syncwarp();
+    if (a.alpha) {
+        double* al = a.alpha + (size_t)model * M;
+        for (int i = lane; i < M; i += 32) {
+            double s = 0;
+            for (int j = 0; j < M; ++j) s += __ldg(Ki + (size_t)i * M + j) * kv[j];
+            al[i] = s;
+        }
+    }
+    if (lane == 0) bulk_s2g_wait_read();                   // the shared buffer must outlive the store's read
+}
+
 // alpha = Kx_inv y  for y [B][3][M]   (constant part of RGP.predict_using_y, RGP.py:252-254)
 __global__ void qrgp_alpha_kernel(int B, int M, const double* Kx_inv, const double* y, double* alpha)
 {
