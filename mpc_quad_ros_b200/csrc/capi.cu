@@ -63,6 +63,7 @@ struct qmpc_solver {
     size_t rsz;                       // sizeof(real)
     double *x0 = nullptr, *yref = nullptr, *yref_e = nullptr, *alpha = nullptr, *xit = nullptr, *uit = nullptr;
     double *u0 = nullptr, *cost = nullptr, *gpX = nullptr, *xt = nullptr, *yt = nullptr;
+    double gp_grid[6] = {0, 0, 0, 0, 0, 0};   // per axis {first basis point, spacing} of an equispaced grid (spacing 0: general path)
     int *status = nullptr, *iters = nullptr, *rounds = nullptr;
     unsigned char* act = nullptr;     // [B][4N] active sets remembered for the warm start
     void *W = nullptr, *fac = nullptr;
@@ -148,6 +149,7 @@ int qmpc_create(const qmpc_config* cfg, qmpc_handle_t* out)
     CU_TRY(cudaMemset(h->rounds, 0, B * 4)); CU_TRY(cudaMemset(h->act, 255, B * N * NU));
     CU_TRY(cudaMemset(h->fail_streak, 0, B * 4));
     if (M) CU_TRY(cudaMemcpy(h->gpX, cfg->gp_X, 3 * M * 8, cudaMemcpyHostToDevice));
+    gp_grid_detect(M ? cfg->gp_X : nullptr, M, h->gp_grid);
     h->x0_src = h->x0; h->alpha_src = h->alpha; h->alpha_stride = 3 * (int)M;
     const size_t smem64 = (size_t)IPM_WARPS * ipm_smem_reals((int)N, true, true) * 8, smem32 = (size_t)IPM_WARPS * ipm_smem_reals((int)N, true, false) * 4;
     if (smem64 > 220 * 1024) return fail(QMPC_ERR_ARG, "n_nodes too large for the shared-memory plan");
@@ -277,6 +279,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
     fill_lin_args(h->cfg, la);
     la.xit = h->xit; la.uit = h->uit; la.yref = h->yref; la.alpha = h->alpha_src; la.alpha_stride = h->alpha_stride;
     la.gpX = h->gpX; la.W = static_cast<real*>(h->W);
+    fill_gp_grid(h->gp_grid, la.mp);
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (h->timing && h->ev.size() < 3 * 8192) {
         CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1)); CU_TRY(cudaEventCreate(&e2));
@@ -287,7 +290,7 @@ static int solve_impl(qmpc_solver* h, void* stream)
         reset_failed_kernel<<<cdiv((long long)B * (N + 1), 256), 256, 0, S(stream)>>>(B, N, h->status, h->yref, h->yref_e, h->xit, h->uit, h->act, h->fail_streak);
         LAUNCH_CHECK();
     }
-    qmpc_linearize_kernel<double, real><<<cdiv((long long)B * N * 16, 128), 128, 0, S(stream)>>>(la);
+    qmpc_linearize_kernel<double, real><<<cdiv((long long)B * N, LIN_NB), LIN_THREADS, 0, S(stream)>>>(la);
     LAUNCH_CHECK();
     if (e1) CU_TRY(cudaEventRecord(e1, S(stream)));
     IpmArgs<real> ia;

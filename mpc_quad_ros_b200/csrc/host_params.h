@@ -1,6 +1,7 @@
 // host_params.h — host-side translation of qmpc_config into kernel argument blocks
 // (shared by capi.cu and the test-only emulation harness).
 #pragma once
+#include <cmath>
 #include "../../include/qmpc.h"
 #include "mpc_kernels.cuh"
 
@@ -25,6 +26,32 @@ inline void fill_model(const qmpc_config& c, ModelParams<real>& mp)
         mp.iL2[d] = real(L != 0.0 ? 1.0 / (L * L) : 0.0);
     }
     mp.M = c.n_basis;
+    for (int d = 0; d < 3; ++d) { mp.gx0[d] = 0; mp.gdx[d] = 0; mp.gidx[d] = 0; mp.gcc[d] = 0; }
+}
+
+// Equispaced basis points (the reference builds them with linspace, GPE.py:127-150) let K1 evaluate the M kernel values of an
+// axis from three exps and a two-term recurrence; grid[d] = {first point, spacing} or spacing 0 when axis d is not equispaced
+// to 1e-12 of its range.  X: host [3][M].
+inline void gp_grid_detect(const double* X, int M, double grid[6])
+{
+    for (int d = 0; d < 3; ++d) {
+        grid[2 * d] = 0; grid[2 * d + 1] = 0;
+        if (!X || M < 2) continue;
+        const double* x = X + (size_t)d * M;
+        const double dx = (x[M - 1] - x[0]) / (M - 1);
+        double span = std::fabs(x[M - 1] - x[0]), dev = 0;
+        for (int i = 0; i < M; ++i) dev = std::fmax(dev, std::fabs(x[i] - (x[0] + i * dx)));
+        if (dx > 0 && std::isfinite(dx) && dev <= 1e-12 * span) { grid[2 * d] = x[0]; grid[2 * d + 1] = dx; }
+    }
+}
+template <typename real>
+inline void fill_gp_grid(const double grid[6], ModelParams<real>& mp)
+{
+    for (int d = 0; d < 3; ++d) {
+        const double dx = grid[2 * d + 1];
+        mp.gx0[d] = real(grid[2 * d]); mp.gdx[d] = real(dx); mp.gidx[d] = real(dx > 0 ? 1.0 / dx : 0.0);
+        mp.gcc[d] = real(std::exp(-dx * dx * double(mp.iL2[d])));
+    }
 }
 
 inline double cfg_dt(const qmpc_config& c) { return c.t_horizon / c.n_nodes; }

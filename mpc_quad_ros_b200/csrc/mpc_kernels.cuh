@@ -49,122 +49,167 @@ struct LinArgs {
     treal* W;             // [B][N][13][16]
 };
 
-// GP mean/slope per body axis.  Five lanes of the 16-lane group work on each axis (lane j: axis j / 5, basis points
-// j % 5, j % 5 + 5, ...; lane 15 idles), so a lane's kernel width / amplitude are fixed and nothing is selected or divided
-// per point.  A lane's basis points and weights do not change over the four RK4 stages: for M <= 20 they are fetched once
-// into registers (GpLane), larger M re-read them (L1) every stage.
-constexpr int GP_LPA = 5;          // lanes per axis
-constexpr int GP_REG = 4;          // basis points per lane kept in registers (M <= GP_LPA * GP_REG)
+// K1 runs in two phases per block of LIN_NB nodes (the primal is evaluated ONCE per node, not once per sensitivity column):
+//   phase A, lane = node:   RK4 of the nominal + GP dynamics; at each of the four stage points the lane leaves what the
+//                           tangent needs (q, r and the velocity-row Jacobian blocks: LIN_SF reals) in shared memory,
+//                           field-major so that the stores are conflict-free, and finally Phi(x_k, u_k);
+//   phase B, 16 lanes/node: lane j carries tile column j (one unit seed) through the four cached stage points with the
+//                           hand-written tangent jvp_cached - every read of a stage field is a broadcast - and stores its column.
+// No shuffles, one block barrier.  The 3M kernel evaluations of the GP are spread over the lanes by construction (each
+// lane owns a node), so nothing is reduced across lanes either.
+constexpr int LIN_NB = 32;                 // nodes per block
+constexpr int LIN_THREADS = 64;
+constexpr int LIN_SF = 31;                 // q4 r3 Cq12 Cv9 Rz3 (model.cuh velocity_jacobian)
+constexpr int LIN_NF = 4 * LIN_SF + NX;    // four stage points + Phi
 
 template <typename real>
-struct GpLane {
-    int d, l;                      // axis (3 = idle lane), first basis point
-    real il2;                      // 1/L^2 of the axis
-    real* xb;                      // shared memory, stride blockDim.x: GP_REG basis points, then GP_REG weights sf^2 * alpha
-};
-
-template <typename real>
-__device__ __forceinline__ void gp_lane_setup(const ModelParams<real>& mp, int j, const double* __restrict__ gpX,
-                                              const double* __restrict__ alpha, real* lane_store, GpLane<real>& g)
+__device__ __forceinline__ void gp_eval(const ModelParams<real>& mp, const double* __restrict__ gpX, const double* __restrict__ alpha,
+                                        const real* vb, real* mu, real* dmu)
 {
-    g.xb = lane_store;
-    g.d = j / GP_LPA; g.l = j - g.d * GP_LPA;
-    const int d = g.d < 3 ? g.d : 0;
-    g.il2 = d == 0 ? mp.iL2[0] : (d == 1 ? mp.iL2[1] : mp.iL2[2]);
-    const real sf2 = d == 0 ? mp.sf2[0] : (d == 1 ? mp.sf2[1] : mp.sf2[2]);
 #pragma unroll
-    for (int t = 0; t < GP_REG; ++t) {
-        const int i = g.l + GP_LPA * t;
-        const bool on = g.d < 3 && i < mp.M;
-        g.xb[t * blockDim.x] = on ? real(__ldg(gpX + d * mp.M + i)) : real(0);
-        g.xb[(GP_REG + t) * blockDim.x] = on ? sf2 * real(__ldg(alpha + d * mp.M + i)) : real(0);
-    }
-}
-
-template <typename real>
-__device__ __forceinline__ void gp_group_eval(const ModelParams<real>& mp, unsigned hmask, const GpLane<real>& g,
-                                              const double* __restrict__ gpX, const double* __restrict__ alpha,
-                                              const real* vb, real* mu, real* dmu)
-{
-    const real v = g.d == 0 ? vb[0] : (g.d == 1 ? vb[1] : vb[2]);
-    real s = 0, ds = 0;
-    if (mp.M <= GP_LPA * GP_REG) {
-#pragma unroll
-        for (int t = 0; t < GP_REG; ++t) {
-            const real e = v - g.xb[t * blockDim.x];
-            const real ka = g.xb[(GP_REG + t) * blockDim.x] * rexp<real>(real(-0.5) * e * g.il2 * e);
-            s += ka; ds -= ka * e * g.il2;
+    for (int d = 0; d < 3; ++d) {
+        const real il2 = mp.iL2[d], sf2 = mp.sf2[d], v = vb[d];
+        const double* X = gpX + d * mp.M;
+        const double* al = alpha + d * mp.M;
+        real s = 0, ds = 0;
+        if (mp.gdx[d] > real(0)) {
+            // equispaced axis: k_m = exp(-(v - X_m)^2 / 2L^2) obeys k_{m+-1} = k_m rho_m, rho_{m+-1} = rho_m exp(-dx^2 / L^2).
+            // Started at the basis point nearest to v and run outwards, every factor is <= 1: the values decay
+            // monotonically (no overflow; underflow is the correct limit).  3 exps per axis instead of M.
+            const real dx = mp.gdx[d], g = dx * il2, cc = mp.gcc[d];
+            real t = (v - mp.gx0[d]) * mp.gidx[d];
+            t = fmin(fmax(t, real(0)), real(mp.M - 1));
+            const int ms = int(rint(t));
+            const real es = v - real(__ldg(X + ms));
+            const real ks = rexp<real>(real(-0.5) * es * il2 * es);
+            real q = real(__ldg(al + ms)) * ks;
+            s = q; q *= es;
+            real k = ks, rho = rexp<real>((es - real(0.5) * dx) * g), e = es;
+            for (int m = ms + 1; m < mp.M; ++m) {
+                k *= rho; rho *= cc; e -= dx;
+                const real ka = real(__ldg(al + m)) * k;
+                s += ka; q = fma(ka, e, q);
+            }
+            k = ks; rho = rexp<real>(-(es + real(0.5) * dx) * g); e = es;
+            for (int m = ms - 1; m >= 0; --m) {
+                k *= rho; rho *= cc; e += dx;
+                const real ka = real(__ldg(al + m)) * k;
+                s += ka; q = fma(ka, e, q);
+            }
+            s *= sf2; ds = -sf2 * il2 * q;
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < mp.M; ++i) {
+                const real e = v - real(__ldg(X + i));
+                const real ka = sf2 * real(__ldg(al + i)) * rexp<real>(real(-0.5) * e * il2 * e);
+                s += ka; ds -= ka * e * il2;
+            }
         }
-    } else if (g.d < 3) {
-        const real sf2 = g.d == 0 ? mp.sf2[0] : (g.d == 1 ? mp.sf2[1] : mp.sf2[2]);
-        const double* X = gpX + g.d * mp.M;
-        const double* al = alpha + g.d * mp.M;
-        for (int i = g.l; i < mp.M; i += GP_LPA) {
-            const real e = v - real(__ldg(X + i));
-            const real ka = sf2 * real(__ldg(al + i)) * rexp<real>(real(-0.5) * e * g.il2 * e);
-            s += ka; ds -= ka * e * g.il2;
-        }
+        mu[d] = s; dmu[d] = ds;
     }
-    mu[0] = half_sum(hmask, g.d == 0 ? s : real(0)); mu[1] = half_sum(hmask, g.d == 1 ? s : real(0)); mu[2] = half_sum(hmask, g.d == 2 ? s : real(0));
-    dmu[0] = half_sum(hmask, g.d == 0 ? ds : real(0)); dmu[1] = half_sum(hmask, g.d == 1 ? ds : real(0)); dmu[2] = half_sum(hmask, g.d == 2 ? ds : real(0));
 }
 
 template <typename real, typename treal = real>
-__global__ void __launch_bounds__(128, 3) qmpc_linearize_kernel(LinArgs<real, treal> a)
+__global__ void __launch_bounds__(LIN_THREADS) qmpc_linearize_kernel(LinArgs<real, treal> a)
 {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int node = gt >> 4, j = gt & 15;
-    if (node >= a.B * a.N) return;                     // whole 16-lane group leaves together
-    const unsigned hmask = 0xffffu << (threadIdx.x & 16);
-    const int b = node / a.N, k = node - b * a.N;
-    const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
-    const double* uk = a.uit + ((size_t)b * a.N + k) * NU;
-    const double* al = a.alpha + (size_t)b * a.alpha_stride;
-    real x[NX], u[NU], du[NU];
+    QMPC_STATIC_SMEM(real, sd, LIN_NF * LIN_NB);       // [field][node of the block]
+    const int tid = threadIdx.x;
+    const int total = a.B * a.N, base = blockIdx.x * LIN_NB;
+    // ---- phase A
+    if (tid < LIN_NB && base + tid < total) {
+        const int node = base + tid, b = node / a.N, k = node - b * a.N;
+        const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
+        const double* uk = a.uit + ((size_t)b * a.N + k) * NU;
+        const double* al = a.alpha + (size_t)b * a.alpha_stride;
+        real x[NX], u[NU], kprev[NX], accx[NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = real(__ldg(xk + i));
+        for (int i = 0; i < NX; ++i) { x[i] = real(__ldg(xk + i)); accx[i] = x[i]; kprev[i] = 0; }
 #pragma unroll
-    for (int i = 0; i < NU; ++i) { u[i] = real(__ldg(uk + i)); du[i] = (i == j) ? real(1) : real(0); }
-    const int sj = (j >= 4 && j < 14) ? j - 1 : -1;    // state index of this lane's x-direction
-    real kprev[NX], dkprev[NX], accx[NX], accd[NX];
+        for (int i = 0; i < NU; ++i) u[i] = real(__ldg(uk + i));
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { kprev[i] = 0; dkprev[i] = 0; accx[i] = x[i]; accd[i] = (i == sj) ? real(1) : real(0); }
-    const real zero3[3] = {0, 0, 0};
-    GpLane<real> gl;
-    QMPC_STATIC_SMEM(real, gp_store, 2 * GP_REG * 128);       // per thread: its basis points and weights (only the thread itself reads them)
-    if (a.mp.M > 0) gp_lane_setup(a.mp, j, a.gpX, al, gp_store + threadIdx.x, gl);
+        for (int s = 0; s < 4; ++s) {
+            const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
+            const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
+            real xs[NX], kk[NX], mu[3] = {0, 0, 0}, dmu[3] = {0, 0, 0};
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
-        const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
-        real xs[NX], dxs[NX], kk[NX], dk[NX], mu[3], dmu[3];
+            for (int i = 0; i < NX; ++i) xs[i] = x[i] + as * kprev[i];
+            if (a.mp.M > 0) {
+                real vb[3];
+                body_velocity(xs, vb);
+                gp_eval(a.mp, a.gpX, al, vb, mu, dmu);
+            }
+            EvalPoint<real> e;
+            eval_f(a.mp, xs, u, mu, dmu, e, kk);
+            real Cq[12], Cv[9];
+            velocity_jacobian(e, Cq, Cv);
+            real* o = sd + (size_t)s * LIN_SF * LIN_NB + tid;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { xs[i] = x[i] + as * kprev[i]; dxs[i] = ((i == sj) ? real(1) : real(0)) + as * dkprev[i]; }
-        if (a.mp.M > 0) {
-            real vb[3];
-            body_velocity(xs, vb);
-            gp_group_eval(a.mp, hmask, gl, a.gpX, al, vb, mu, dmu);
-        } else {
+            for (int i = 0; i < 4; ++i) o[i * LIN_NB] = e.q[i];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { mu[i] = zero3[i]; dmu[i] = zero3[i]; }
+            for (int i = 0; i < 3; ++i) { o[(4 + i) * LIN_NB] = e.r[i]; o[(28 + i) * LIN_NB] = e.R[3 * i + 2]; }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) o[(7 + i) * LIN_NB] = Cq[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) o[(19 + i) * LIN_NB] = Cv[i];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { accx[i] += ws * kk[i]; kprev[i] = kk[i]; }
         }
-        EvalPoint<real> e;
-        eval_f(a.mp, xs, u, mu, dmu, e, kk);
-        jvp_f(a.mp, e, dxs, du, dk);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { accx[i] += ws * kk[i]; accd[i] += ws * dk[i]; kprev[i] = kk[i]; dkprev[i] = dk[i]; }
+        for (int i = 0; i < NX; ++i) sd[(size_t)(4 * LIN_SF + i) * LIN_NB + tid] = accx[i];
     }
-    if (j == 14) {                                     // b = Phi - x_{k+1}
+    __syncthreads();
+    // ---- phase B
+    const int j = tid & 15;
+    const int sj = (j >= 4 && j < 14) ? j - 1 : -1;    // state index of this lane's x-direction
+    // input columns (j < 4): thrust enters v_dot through R[:,2] T/m, the body torques are constants of the column
+    const real usel = j < 4 ? a.mp.thrust_over_mass : real(0);
+    const int ju = j < 4 ? j : 0;
+    const real tq[3] = {j < 4 ? a.mp.T * a.mp.yf[ju] * a.mp.invJ[0] : real(0), j < 4 ? -a.mp.T * a.mp.xf[ju] * a.mp.invJ[1] : real(0),
+                        j < 4 ? a.mp.T * a.mp.zt[ju] * a.mp.invJ[2] : real(0)};
+    const real kr[3] = {a.mp.Jc[0] * a.mp.invJ[0], a.mp.Jc[1] * a.mp.invJ[1], a.mp.Jc[2] * a.mp.invJ[2]};
+    for (int it = 0; it < LIN_NB * 16 / LIN_THREADS; ++it) {
+        const int nl = it * (LIN_THREADS / 16) + (tid >> 4), node = base + nl;
+        if (node >= total) continue;
+        const int b = node / a.N, k = node - b * a.N;
+        real dkprev[NX], accd[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) accd[i] = accx[i] - real(__ldg(xk + NX + i));
-    } else if (j == 15) {                              // q = dt W_x (x_k - xref_k)
-        const double* yr = a.yref + ((size_t)b * a.N + k) * NY;
+        for (int i = 0; i < NX; ++i) { dkprev[i] = 0; accd[i] = (i == sj) ? real(1) : real(0); }
+        if (j < 14) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) accd[i] = a.Qd[i] * (x[i] - real(__ldg(yr + i)));
+            for (int s = 0; s < 4; ++s) {
+                const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
+                const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
+                const real* o = sd + (size_t)s * LIN_SF * LIN_NB + nl;
+                real q[4], r[3], Cq[12], Cv[9], uz[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = o[i * LIN_NB];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { r[i] = o[(4 + i) * LIN_NB]; uz[i] = usel * o[(28 + i) * LIN_NB]; }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) Cq[i] = o[(7 + i) * LIN_NB];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Cv[i] = o[(19 + i) * LIN_NB];
+                real dxs[NX], dk[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) dxs[i] = ((i == sj) ? real(1) : real(0)) + as * dkprev[i];
+                jvp_cached(q, r, Cq, Cv, uz, kr, tq, dxs, dk);
+#pragma unroll
+                for (int i = 0; i < NX; ++i) { accd[i] += ws * dk[i]; dkprev[i] = dk[i]; }
+            }
+        } else if (j == 14) {                              // b = Phi - x_{k+1}
+            const double* xn = a.xit + ((size_t)b * (a.N + 1) + k + 1) * NX;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) accd[i] = sd[(size_t)(4 * LIN_SF + i) * LIN_NB + nl] - real(__ldg(xn + i));
+        } else {                                           // q = dt W_x (x_k - xref_k)
+            const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
+            const double* yr = a.yref + ((size_t)b * a.N + k) * NY;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) accd[i] = a.Qd[i] * (real(__ldg(xk + i)) - real(__ldg(yr + i)));
+        }
+        treal* Wt = a.W + (size_t)node * WT;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) Wt[i * WR + j] = treal(accd[i]);
     }
-    treal* Wt = a.W + (size_t)node * WT;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) Wt[i * WR + j] = treal(accd[i]);
 }
 
 // ------------------------------------------------------------------------------------------ K2

@@ -18,8 +18,13 @@ static int run_solve(const HostOcp* o, const double* x0, const double* yref, con
     LinArgs<double, real> la;
     fill_lin_args(*o, la);
     la.xit = xit; la.uit = uit; la.yref = yref; la.alpha = alpha; la.gpX = o->gp_X; la.W = W.data();
-    const unsigned threads = 128, total = (unsigned)B * N * 16;
-    emu::launch((total + threads - 1) / threads, threads, 0, [&]() { qmpc_linearize_kernel<double, real>(la); });
+    {
+        double grid[6];
+        gp_grid_detect(o->n_basis ? o->gp_X : nullptr, o->n_basis, grid);      // as qmpc_create does
+        if (getenv("EMU_GP_DIRECT")) for (double& g : grid) g = 0;              // test hook: force the general (one exp per value) path
+        fill_gp_grid(grid, la.mp);
+    }
+    emu::launch(((unsigned)B * N + LIN_NB - 1) / LIN_NB, LIN_THREADS, 0, [&]() { qmpc_linearize_kernel<double, real>(la); });
     if (getenv("EMU_ROUND_TILES_FP32"))      // experiment: how much of the fp32 build's error is the rounding of the tile data alone
         for (auto& v : W) v = real(float(v));
     IpmArgs<real> ia;

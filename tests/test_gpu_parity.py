@@ -32,7 +32,9 @@ def _solve_batch(sc, B, N, gp, precision=64, quad_name="hummingbird", mu_tol=0.0
     quad = Quadrotor3D(drag=True, batch=B)
     quad = quad.set_hummingbird_params() if quad_name == "hummingbird" else quad.set_logged_pysim_params()
     gpe = None
-    if gp is not None:
+    if gp is not None and policy.pop("basis_vectors", False):
+        gpe = GPEnsemble.frombasisvectors([gp.X[d] for d in range(3)], [np.zeros(gp.M)] * 3, [None] * 3, [list(gp.theta[d]) for d in range(3)], batch=B)
+    elif gp is not None:
         gpe = GPEnsemble.fromrange([(gp.X[d, 0], gp.X[d, -1]) for d in range(3)], [gp.M] * 3, theta=list(gp.theta[0]), batch=B)
     opt = quad_optimizer(quad, t_horizon=1.0, n_nodes=N, gpe=gpe, precision=precision, ipm_mu_tol=mu_tol, **policy)
     opt.set_iterate(torch.as_tensor(sc["xit"]), torch.as_tensor(sc["uit"]))
@@ -74,6 +76,35 @@ def test_solve_fp64_vs_oracle(N, M, seed):
     nact = ((uo < 1e-9) | (uo > 1 - 1e-9)).sum()
     assert nact > 0 or N < 3                           # the batch does exercise active thrust limits
     print(f"N={N} M={M}: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e} ipm iters mean={it.mean():.1f} (oracle {ito.mean():.1f})")
+
+
+@pytest.mark.parametrize("layout", ["scattered", "narrow_kernel", "velocities_off_grid", "two_points"])
+def test_gp_basis_point_layouts_vs_oracle(layout):
+    """K1 evaluates an equispaced axis (linspace, GPE.fromrange) with three exps and a recurrence started at the basis point
+    nearest to the velocity, any other layout with one exp per kernel value: scattered points take the general path; a
+    length-scale far below the spacing, velocities outside the grid and a two-point grid stress the recurrence"""
+    B, N, M, dt = 48, 20, 20, 1.0 / 20
+    rng = np.random.default_rng(5)
+    quad = orc.quad_hummingbird()
+    if layout == "scattered":
+        X = np.sort(rng.uniform(-10, 10, (3, M)), axis=1)
+        gp = orc.GPSpec(X, np.array((3.0, 0.1, 0.01)))
+    elif layout == "narrow_kernel":
+        gp = orc.GPSpec(np.tile(np.linspace(-10, 10, M), (3, 1)), np.array((0.3, 0.5, 0.01)))
+    elif layout == "velocities_off_grid":
+        gp = orc.GPSpec(np.tile(np.linspace(-0.5, 0.5, M), (3, 1)), np.array((0.2, 0.3, 0.01)))
+    else:
+        M = 2
+        gp = orc.GPSpec(np.tile(np.linspace(-3, 3, M), (3, 1)), np.array((3.0, 0.1, 0.01)))
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=31)
+    x, u, cost, st, it = _solve_batch(sc, B, N, gp, basis_vectors=True)
+    xo, uo, co, ito = oracle_solve_batch(sc, quad, dt, N, gp)
+    assert (st == 0).all(), st
+    assert u_rel(u, uo) < 1e-7 and x_rel(x, xo) < 1e-7, (layout, u_rel(u, uo), x_rel(x, xo))
+    # the GP term does matter in these problems: the nominal model gives a different answer
+    xn, un, _, _, _ = _solve_batch(sc, B, N, None)
+    assert u_rel(un, uo) > 1e-5 or layout == "velocities_off_grid", u_rel(un, uo)
+    print(f"{layout}: u_rel={u_rel(u, uo):.2e} x_rel={x_rel(x, xo):.2e}; nominal model differs by {u_rel(un, uo):.2e}")
 
 
 def test_solve_full_baseline_batch_subset_vs_oracle():

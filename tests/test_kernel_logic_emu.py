@@ -184,3 +184,32 @@ def test_emulated_build_without_tile_ring_matches_oracle(variant):
     x2, u2 = xe.copy(), ue.copy()
     r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=r1["act"].copy(), variant=variant, flavour="noring")
     assert (r2["status"] == 0).all() and u_rel(u2, uo2) < TOL[variant] and x_rel(x2, xo2) < TOL[variant]
+
+
+@pytest.mark.parametrize("layout", ["equispaced", "equispaced_forced_general", "scattered", "narrow_kernel", "velocities_off_grid"])
+def test_emulated_gp_basis_point_layouts(layout, monkeypatch):
+    """K1's GP term: an equispaced axis (linspace) is evaluated with three exps and a recurrence that starts at the basis
+    point nearest to the velocity; any other layout (or EMU_GP_DIRECT, the test hook that forces it) takes one exp per kernel
+    value.  Both must land on the oracle's minimiser, also with a length-scale far below the spacing and with velocities
+    outside the grid."""
+    B, N, M = 3, 10, 20
+    dt = 1.0 / N
+    rng = np.random.default_rng(9)
+    quad = orc.quad_hummingbird()
+    if layout == "scattered":
+        gp = orc.GPSpec(np.sort(rng.uniform(-10, 10, (3, M)), axis=1), np.array((3.0, 0.1, 0.01)))
+    elif layout == "narrow_kernel":
+        gp = orc.GPSpec(np.tile(np.linspace(-10, 10, M), (3, 1)), np.array((0.3, 0.5, 0.01)))
+    elif layout == "velocities_off_grid":
+        gp = orc.GPSpec(np.tile(np.linspace(-0.5, 0.5, M), (3, 1)), np.array((0.2, 0.3, 0.01)))
+    else:
+        gp = make_gp(M)
+    if layout == "equispaced_forced_general":
+        monkeypatch.setenv("EMU_GP_DIRECT", "1")
+    sc = random_ocp_batch(B, N, dt, quad, gp, seed=13)
+    cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
+    xe, ue = sc["xit"].copy(), sc["uit"].copy()
+    r = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=1)
+    xo, uo, cost, iters = oracle_solve_batch(sc, quad, dt, N, gp)
+    assert (r["status"] == 0).all()
+    assert u_rel(ue, uo) < 1e-8 and x_rel(xe, xo) < 1e-8, (layout, u_rel(ue, uo), x_rel(xe, xo))
