@@ -85,12 +85,14 @@ __device__ __forceinline__ void gp_eval(const ModelParams<real>& mp, const doubl
             real q = real(__ldg(al + ms)) * ks;
             s = q; q *= es;
             real k = ks, rho = rexp<real>((es - real(0.5) * dx) * g), e = es;
+#pragma unroll 4
             for (int m = ms + 1; m < mp.M; ++m) {
                 k *= rho; rho *= cc; e -= dx;
                 const real ka = real(__ldg(al + m)) * k;
                 s += ka; q = fma(ka, e, q);
             }
             k = ks; rho = rexp<real>(-(es + real(0.5) * dx) * g); e = es;
+#pragma unroll 4
             for (int m = ms - 1; m >= 0; --m) {
                 k *= rho; rho *= cc; e += dx;
                 const real ka = real(__ldg(al + m)) * k;
@@ -171,6 +173,10 @@ __global__ void __launch_bounds__(LIN_THREADS) qmpc_linearize_kernel(LinArgs<rea
         const int nl = it * (LIN_THREADS / 16) + (tid >> 4), node = base + nl;
         if (node >= total) continue;
         const int b = node / a.N, k = node - b * a.N;
+        if (j >= 12) {       // columns 14 / 15 read x_k, x_{k+1}, yref_k from global memory after the tangent columns: warm L1 now
+            const double* late = j < 14 ? a.xit + ((size_t)b * (a.N + 1) + k) * NX : a.yref + ((size_t)b * a.N + k) * NY;
+            prefetch_l1(late + (j & 1) * 16);
+        }
         real dkprev[NX], accd[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) { dkprev[i] = 0; accd[i] = (i == sj) ? real(1) : real(0); }
