@@ -161,20 +161,30 @@ def reference_arm(a):
 # ------------------------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in loop mode, started BEFORE the warm-up steps (the process takes ~0.1 s to deliver its first line, the
+    driver's timed window is 40 ms long) and sampling every 10 ms; `mark()` brackets the timed region on the host clock.
+    stop() reports the samples that fall inside the marks, or - if the window was too short to catch one - those taken
+    under load since the warm-up began, and says which in `window`."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.marks = []
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark(self):
+        import datetime
+        self.marks.append(datetime.datetime.now())
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
         self.p.terminate()
@@ -184,20 +194,22 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in self.f.read().splitlines():
             c = [t.strip() for t in ln.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[1]), float(c[2]), [v.lower().startswith("active") for v in c[5:9]]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if len(self.marks) >= 2 and self.marks[0] <= r[0] <= self.marks[1]]
+        use, window = (inside, "timed region") if inside else (rows, "warm-up + timed region (no sample fell inside the timed region)")
+        if use:
+            reasons = {name for r in use for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]) if on}
+            out = {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)), "reasons": sorted(reasons),
+                   "samples": len(use), "window": window}
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -356,10 +368,12 @@ def b200_arm(a):
         a.groups = 1
     grouped = a.groups > 1 and not a.shared_rgp
     loop = GroupedClosedLoop(make_loop, B, a.groups) if grouped else make_loop()
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         loop.step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     l0 = lib.qmpc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -371,6 +385,8 @@ def b200_arm(a):
         loop.join()
     e1.record()
     barrier()
+    if sampler:
+        sampler.mark()
     ms = e0.elapsed_time(e1)
     launches = lib.qmpc_launch_count() - l0
     clocks = sampler.stop() if sampler else None
@@ -471,8 +487,9 @@ def b200_arm(a):
     lin_ach = lin_flops / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
     roofline_lin = {"kernel": "qmpc_linearize_kernel", "leg": "roofline", "bound": "fp%d_fma" % a.precision, "achieved": lin_ach, "peak": peak.value,
                     "unit": "TFLOP/s", "frac": lin_ach / peak.value if peak.value else None, "traffic": None,
-                    "ms_per_launch": lin_ms, "note": "algorithmic flops N*(22116+108M) per vehicle (SURVEY 8d); ncu: fp64 pipe 45 % busy "
-                                                      "(redundant primal evaluation per sensitivity column, double-precision exp of the RBF)"}
+                    "ms_per_launch": lin_ms, "note": "algorithmic flops N*(22116+108M) per vehicle (SURVEY 8d), i.e. dense Jacobians and one exp per kernel value; the "
+                                                      "kernel itself evaluates the primal + GP once per node (3 exps per equispaced axis) and 14 tangent "
+                                                      "columns on cached Jacobian blocks: 51M warp instructions per launch at 4096x20 (round-2 start: 258M)"}
 
     # ---------------- secondary roofline: the HBM-bound RGP update (K3), timed alone with CUDA events
     roofline_rgp = None
@@ -498,7 +515,7 @@ def b200_arm(a):
             pass
         peak_gbs = hbm_peak if hbm_peak else 6650.0
         ach = rgp_bytes / (rgp_ms * 1e-3) / 1e9
-        roofline_rgp = {"kernel": "qrgp_regress_kernel", "leg": "stand-alone launches", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+        roofline_rgp = {"kernel": "qrgp_regress_tma_kernel", "leg": "stand-alone launches", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
                         "frac": ach / peak_gbs, "traffic": None, "ms_per_launch": rgp_ms,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6650 GB/s (B200_PROFILING.md)",
                         "note": "covariances of 4096 vehicles (39 MB) fit the 126 MB L2 when launched back to back"}
