@@ -1,7 +1,8 @@
 // mpc_kernels.cuh — the two kernels behind qmpc_solve (one SQP-RTI iteration per vehicle).
 //
 //   K1  qmpc_linearize_kernel : RK4 + forward sensitivities (incl. GP Jacobian) at the N nodes of every
-//       vehicle.  16 lanes per node, one sensitivity column per lane.  Replaces CasADi expl_vde_forw +
+//       vehicle.  Two phases: the primal (with the GP term) once per node, then one sensitivity column per lane on
+//       cached Jacobian blocks (see LIN_NB below).  Replaces CasADi expl_vde_forw +
 //       acados ERK inside AcadosOcpSolver.solve() (reference src/quad_opt.py:333, model :164-262).
 //   K2  qmpc_ipm_kernel       : Gauss-Newton QP (LINEAR_LS cost scaled by dt, x0 pinned, box on u) solved by a
 //       Mehrotra predictor-corrector IPM whose Newton systems are Riccati recursions; one OCP per warp.
