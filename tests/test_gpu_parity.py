@@ -949,3 +949,27 @@ def test_reference_semantics_without_reset_on_fail():
         x1, u1 = (t.cpu().numpy() for t in opt.get_iterate())
         assert np.isnan(x1[2, 5, 2])
         assert (opt.fail_streak().cpu().numpy() == 0).all()
+
+
+@pytest.mark.parametrize("M", [64, 33, 100, 2])
+def test_rgp_regress_kernel_dispatch_sizes(M):
+    """qrgp_regress picks its kernel by the basis size: the TMA-staged one with 8 / 2 / 1 warps per CTA for even M <= 64
+    (M = 20 / 50 are covered by the fixtures above, 64 is the one-warp-per-CTA case, 2 the smallest), the streaming one
+    for odd or larger M; every branch against the C oracle's RGP.regress (itself pinned by the reference's numpy code)"""
+    _, _, GPEnsemble = _pkg()
+    B, T = 7, 12
+    rng = np.random.default_rng(M)
+    theta = [3.0, 0.1, 0.01]
+    gpe = GPEnsemble.fromrange([(-10, 10)] * 3, [M] * 3, theta=theta, batch=B)
+    X = np.tile(np.linspace(-10, 10, M), (3, 1))
+    pri = [orc.rgp_prior(X[d], np.array(theta)) for d in range(3)]
+    mu = np.zeros((B, 3, M)); Cm = np.stack([np.stack([pri[d][0] for d in range(3)])] * B)
+    for t in range(T):
+        xt, yt = rng.uniform(-9, 9, (B, 3)), rng.standard_normal((B, 3))
+        mg, Cg = gpe.regress(torch.as_tensor(xt), torch.as_tensor(yt))
+        for b in range(B):
+            for d in range(3):
+                orc.rgp_regress(X[d], np.array(theta), pri[d][1], mu[b, d], Cm[b, d], xt[b, d], yt[b, d])     # in place
+    assert rel_err(mg.cpu().numpy(), mu) < TOL_RGP and rel_err(Cg.cpu().numpy(), Cm) < TOL_RGP
+    al = gpe.alpha_tensor().cpu().numpy()
+    assert rel_err(al, np.einsum("dij,bdj->bdi", np.stack([p[1] for p in pri]), mu)) < 1e-8
