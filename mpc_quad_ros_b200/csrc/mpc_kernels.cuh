@@ -112,110 +112,119 @@ __device__ __forceinline__ void gp_eval(const ModelParams<real>& mp, const doubl
     }
 }
 
+// phase A for one node: o = field 0 of the node inside its chunk of LIN_NB nodes (fields LIN_NB reals apart)
+template <typename real, typename treal>
+__device__ __forceinline__ void lin_primal(const LinArgs<real, treal>& a, int node, real* o)
+{
+    const int b = node / a.N, k = node - b * a.N;
+    const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
+    const double* uk = a.uit + ((size_t)b * a.N + k) * NU;
+    const double* al = a.alpha + (size_t)b * a.alpha_stride;
+    real x[NX], u[NU], kprev[NX], accx[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { x[i] = real(__ldg(xk + i)); accx[i] = x[i]; kprev[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = real(__ldg(uk + i));
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
+        const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
+        real xs[NX], kk[NX], mu[3] = {0, 0, 0}, dmu[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xs[i] = x[i] + as * kprev[i];
+        if (a.mp.M > 0) {
+            real vb[3];
+            body_velocity(xs, vb);
+            gp_eval(a.mp, a.gpX, al, vb, mu, dmu);
+        }
+        EvalPoint<real> e;
+        eval_f(a.mp, xs, u, mu, dmu, e, kk);
+        real Cq[12], Cv[9];
+        velocity_jacobian(e, Cq, Cv);
+        real* os = o + (size_t)s * LIN_SF * LIN_NB;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) os[i * LIN_NB] = e.q[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { os[(4 + i) * LIN_NB] = e.r[i]; os[(28 + i) * LIN_NB] = e.R[3 * i + 2]; }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) os[(7 + i) * LIN_NB] = Cq[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) os[(19 + i) * LIN_NB] = Cv[i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { accx[i] += ws * kk[i]; kprev[i] = kk[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) o[(size_t)(4 * LIN_SF + i) * LIN_NB] = accx[i];
+}
+
+// phase B for tile column j of one node
+template <typename real, typename treal>
+__device__ __forceinline__ void lin_tangent(const LinArgs<real, treal>& a, int node, int j, const real* o)
+{
+    const int sj = (j >= 4 && j < 14) ? j - 1 : -1;    // state index of this lane's x-direction
+    const int b = node / a.N, k = node - b * a.N;
+    if (j >= 12) {       // columns 14 / 15 read x_k, x_{k+1}, yref_k from global memory after the tangent columns: warm L1 now
+        const double* late = j < 14 ? a.xit + ((size_t)b * (a.N + 1) + k) * NX : a.yref + ((size_t)b * a.N + k) * NY;
+        prefetch_l1(late + (j & 1) * 16);
+    }
+    real dkprev[NX], accd[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { dkprev[i] = 0; accd[i] = (i == sj) ? real(1) : real(0); }
+    if (j < 14) {
+        // input columns (j < 4): thrust enters v_dot through R[:,2] T/m, the body torques are constants of the column
+        const real usel = j < 4 ? a.mp.thrust_over_mass : real(0);
+        const int ju = j < 4 ? j : 0;
+        const real tq[3] = {j < 4 ? a.mp.T * a.mp.yf[ju] * a.mp.invJ[0] : real(0), j < 4 ? -a.mp.T * a.mp.xf[ju] * a.mp.invJ[1] : real(0),
+                            j < 4 ? a.mp.T * a.mp.zt[ju] * a.mp.invJ[2] : real(0)};
+        const real kr[3] = {a.mp.Jc[0] * a.mp.invJ[0], a.mp.Jc[1] * a.mp.invJ[1], a.mp.Jc[2] * a.mp.invJ[2]};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
+            const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
+            const real* os = o + (size_t)s * LIN_SF * LIN_NB;
+            real q[4], r[3], Cq[12], Cv[9], uz[3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = os[i * LIN_NB];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { r[i] = os[(4 + i) * LIN_NB]; uz[i] = usel * os[(28 + i) * LIN_NB]; }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Cq[i] = os[(7 + i) * LIN_NB];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Cv[i] = os[(19 + i) * LIN_NB];
+            real dxs[NX], dk[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) dxs[i] = ((i == sj) ? real(1) : real(0)) + as * dkprev[i];
+            jvp_cached(q, r, Cq, Cv, uz, kr, tq, dxs, dk);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { accd[i] += ws * dk[i]; dkprev[i] = dk[i]; }
+        }
+    } else if (j == 14) {                              // b = Phi - x_{k+1}
+        const double* xn = a.xit + ((size_t)b * (a.N + 1) + k + 1) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) accd[i] = o[(size_t)(4 * LIN_SF + i) * LIN_NB] - real(__ldg(xn + i));
+    } else {                                           // q = dt W_x (x_k - xref_k)
+        const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
+        const double* yr = a.yref + ((size_t)b * a.N + k) * NY;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) accd[i] = a.Qd[i] * (real(__ldg(xk + i)) - real(__ldg(yr + i)));
+    }
+    treal* Wt = a.W + (size_t)node * WT;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) Wt[i * WR + j] = treal(accd[i]);
+}
+
 template <typename real, typename treal = real>
 __global__ void __launch_bounds__(LIN_THREADS) qmpc_linearize_kernel(LinArgs<real, treal> a)
 {
     QMPC_STATIC_SMEM(real, sd, LIN_NF * LIN_NB);       // [field][node of the block]
     const int tid = threadIdx.x;
     const int total = a.B * a.N, base = blockIdx.x * LIN_NB;
-    // ---- phase A
-    if (tid < LIN_NB && base + tid < total) {
-        const int node = base + tid, b = node / a.N, k = node - b * a.N;
-        const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
-        const double* uk = a.uit + ((size_t)b * a.N + k) * NU;
-        const double* al = a.alpha + (size_t)b * a.alpha_stride;
-        real x[NX], u[NU], kprev[NX], accx[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { x[i] = real(__ldg(xk + i)); accx[i] = x[i]; kprev[i] = 0; }
-#pragma unroll
-        for (int i = 0; i < NU; ++i) u[i] = real(__ldg(uk + i));
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
-            const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
-            real xs[NX], kk[NX], mu[3] = {0, 0, 0}, dmu[3] = {0, 0, 0};
-#pragma unroll
-            for (int i = 0; i < NX; ++i) xs[i] = x[i] + as * kprev[i];
-            if (a.mp.M > 0) {
-                real vb[3];
-                body_velocity(xs, vb);
-                gp_eval(a.mp, a.gpX, al, vb, mu, dmu);
-            }
-            EvalPoint<real> e;
-            eval_f(a.mp, xs, u, mu, dmu, e, kk);
-            real Cq[12], Cv[9];
-            velocity_jacobian(e, Cq, Cv);
-            real* o = sd + (size_t)s * LIN_SF * LIN_NB + tid;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i * LIN_NB] = e.q[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { o[(4 + i) * LIN_NB] = e.r[i]; o[(28 + i) * LIN_NB] = e.R[3 * i + 2]; }
-#pragma unroll
-            for (int i = 0; i < 12; ++i) o[(7 + i) * LIN_NB] = Cq[i];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) o[(19 + i) * LIN_NB] = Cv[i];
-#pragma unroll
-            for (int i = 0; i < NX; ++i) { accx[i] += ws * kk[i]; kprev[i] = kk[i]; }
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) sd[(size_t)(4 * LIN_SF + i) * LIN_NB + tid] = accx[i];
-    }
+    if (tid < LIN_NB && base + tid < total) lin_primal(a, base + tid, sd + tid);
     __syncthreads();
-    // ---- phase B
     const int j = tid & 15;
-    const int sj = (j >= 4 && j < 14) ? j - 1 : -1;    // state index of this lane's x-direction
-    // input columns (j < 4): thrust enters v_dot through R[:,2] T/m, the body torques are constants of the column
-    const real usel = j < 4 ? a.mp.thrust_over_mass : real(0);
-    const int ju = j < 4 ? j : 0;
-    const real tq[3] = {j < 4 ? a.mp.T * a.mp.yf[ju] * a.mp.invJ[0] : real(0), j < 4 ? -a.mp.T * a.mp.xf[ju] * a.mp.invJ[1] : real(0),
-                        j < 4 ? a.mp.T * a.mp.zt[ju] * a.mp.invJ[2] : real(0)};
-    const real kr[3] = {a.mp.Jc[0] * a.mp.invJ[0], a.mp.Jc[1] * a.mp.invJ[1], a.mp.Jc[2] * a.mp.invJ[2]};
     for (int it = 0; it < LIN_NB * 16 / LIN_THREADS; ++it) {
         const int nl = it * (LIN_THREADS / 16) + (tid >> 4), node = base + nl;
-        if (node >= total) continue;
-        const int b = node / a.N, k = node - b * a.N;
-        if (j >= 12) {       // columns 14 / 15 read x_k, x_{k+1}, yref_k from global memory after the tangent columns: warm L1 now
-            const double* late = j < 14 ? a.xit + ((size_t)b * (a.N + 1) + k) * NX : a.yref + ((size_t)b * a.N + k) * NY;
-            prefetch_l1(late + (j & 1) * 16);
-        }
-        real dkprev[NX], accd[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { dkprev[i] = 0; accd[i] = (i == sj) ? real(1) : real(0); }
-        if (j < 14) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const real as = s == 0 ? real(0) : (s == 3 ? a.dt : a.dt * real(0.5));
-                const real ws = (s == 0 || s == 3) ? a.dt / real(6) : a.dt / real(3);
-                const real* o = sd + (size_t)s * LIN_SF * LIN_NB + nl;
-                real q[4], r[3], Cq[12], Cv[9], uz[3];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) q[i] = o[i * LIN_NB];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) { r[i] = o[(4 + i) * LIN_NB]; uz[i] = usel * o[(28 + i) * LIN_NB]; }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) Cq[i] = o[(7 + i) * LIN_NB];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Cv[i] = o[(19 + i) * LIN_NB];
-                real dxs[NX], dk[NX];
-#pragma unroll
-                for (int i = 0; i < NX; ++i) dxs[i] = ((i == sj) ? real(1) : real(0)) + as * dkprev[i];
-                jvp_cached(q, r, Cq, Cv, uz, kr, tq, dxs, dk);
-#pragma unroll
-                for (int i = 0; i < NX; ++i) { accd[i] += ws * dk[i]; dkprev[i] = dk[i]; }
-            }
-        } else if (j == 14) {                              // b = Phi - x_{k+1}
-            const double* xn = a.xit + ((size_t)b * (a.N + 1) + k + 1) * NX;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) accd[i] = sd[(size_t)(4 * LIN_SF + i) * LIN_NB + nl] - real(__ldg(xn + i));
-        } else {                                           // q = dt W_x (x_k - xref_k)
-            const double* xk = a.xit + ((size_t)b * (a.N + 1) + k) * NX;
-            const double* yr = a.yref + ((size_t)b * a.N + k) * NY;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) accd[i] = a.Qd[i] * (real(__ldg(xk + i)) - real(__ldg(yr + i)));
-        }
-        treal* Wt = a.W + (size_t)node * WT;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) Wt[i * WR + j] = treal(accd[i]);
+        if (node < total) lin_tangent(a, node, j, sd + nl);
     }
 }
 
