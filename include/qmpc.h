@@ -61,7 +61,9 @@ typedef struct {
     double we_diag[13];  /* terminal weights diag(W_e) (quad_opt.py:130)                               */
     double lbu, ubu;     /* input box (quad_opt.py:142-143)                                            */
     double gp_theta[9];  /* per axis (L, sigma_f, sigma_n) (RGP.py:106)                                */
-    const double *gp_X;  /* host [3][M] basis points, may be NULL when n_basis == 0                    */
+    const double *gp_X;  /* host [3][M] basis points, may be NULL when n_basis == 0.  Any layout is accepted; an axis
+                            whose points are equispaced (linspace, what GPEnsemble.fromrange builds: GPE.py:127-150) is
+                            detected here and its M kernel values are evaluated from 3 exps by recurrence            */
     /* ---- solver policy, per handle (every field: 0 -> library default).  The reference has no counterpart: acados
      * cold-starts HPIPM every step and ignores its status (quad_opt.py:333, _acados_ocp.json qp_solver_warm_start 0). */
     int solver_variant;    /* 0 -> auto: Riccati screening launch + dense condensed launch for fp64 with N <= 21, the
