@@ -128,6 +128,35 @@ __device__ __forceinline__ void bulk_wait_warp(unsigned long long* bar, unsigned
 #endif
 }
 
+// ---- completion flags between the warps of one CTA (a producer warp publishes shared-memory data, consumer warps wait
+// for it without a CTA barrier): an mbarrier that every lane of the producer warp arrives on once per generation
+// (arrive = release, try_wait = acquire at CTA scope; the waiters suspend in hardware).  Generation g completes phase g,
+// whose parity is g & 1.  Host emulation: a 64-bit arrival counter, 32 arrivals per generation.
+__device__ __forceinline__ void flag_init(unsigned long long* bar)
+{
+#ifdef QMPC_EMU
+    __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST);
+#else
+    mbar_init(bar, 32);
+#endif
+}
+__device__ __forceinline__ void flag_arrive(unsigned long long* bar)
+{
+#ifdef QMPC_EMU
+    __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST);
+#else
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void flag_wait(unsigned long long* bar, unsigned generation)
+{
+#ifdef QMPC_EMU
+    while (__atomic_load_n(bar, __ATOMIC_ACQUIRE) < 32ull * (generation + 1ull)) std::this_thread::yield();
+#else
+    mbar_wait(bar, generation & 1u);
+#endif
+}
+
 template <typename real> __device__ __forceinline__ real rrsqrt(real x);
 #ifdef QMPC_EMU
 template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return 1.0 / sqrt(x); }

@@ -339,6 +339,18 @@ struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal; inputs / outputs 
         l32 = (real(M[14]) - l30 * l20 - l31 * l21) * i2;
         i3 = rrsqrt<real>(real(M[15]) - l30 * l30 - l31 * l31 - l32 * l32);
     }
+    // Keeps the factorisation where it is written: without it the compiler sinks factor() into each of the divergent
+    // branches that use the result (tile rows / right-hand side / diagonal), and a warp then runs the 4x4 Cholesky's
+    // dependent chain once per branch, one after the other (seen in the SASS of the dense kernel: three copies).
+    __device__ __forceinline__ void pin()
+    {
+#ifndef QMPC_EMU
+        if constexpr (sizeof(real) == 8)
+            asm volatile("" : "+d"(l10), "+d"(l20), "+d"(l21), "+d"(l30), "+d"(l31), "+d"(l32), "+d"(i0), "+d"(i1), "+d"(i2), "+d"(i3));
+        else
+            asm volatile("" : "+f"(l10), "+f"(l20), "+f"(l21), "+f"(l30), "+f"(l31), "+f"(l32), "+f"(i0), "+f"(i1), "+f"(i2), "+f"(i3));
+#endif
+    }
     template <typename TI, typename TO>
     __device__ __forceinline__ void fsolve(const TI* v, TO* z) const   // Lam z = v
     {

@@ -32,7 +32,7 @@ struct DenseArgs {
 //   Gc[2][DN_CH][13][GS]      sqrt(Q)-scaled impulse-response columns of DN_CH stages, double-buffered
 //   evc[2][DN_CH][16]         sqrt(Q)-scaled free response + (iterate - reference) of those stages
 struct DenseLayout {
-    int E, T, GS, Ht, Lt, tiles, Gc, evc, sq, sml, dxs, vec, total;
+    int E, T, GS, Ht, Lt, tiles, Gc, evc, sq, sml, cbar, dxs, vec, total;
 };
 constexpr int DN_NVEC = 18;
 constexpr int DN_CH = 3;            // stages per condensing chunk (one CTA barrier per chunk)
@@ -45,7 +45,8 @@ __host__ __device__ inline DenseLayout dense_layout(int N)
     const int cond = L.evc + 2 * DN_CH * 16, fact = 2 * L.T * TS;
     L.sq = cond > fact ? cond : fact;
     L.sml = L.sq + 32;                   // small: wv(16) xp(16) reduction scratch(16) control words(8) mbarrier(8)
-    L.dxs = L.sml + 64;
+    L.cbar = L.sml + 64;                 // one completion flag (mbarrier) per block column of the factorisation
+    L.dxs = L.cbar + DN_MAX_N + 3;
     L.vec = (L.dxs + 13 * (N + 1) + 1) & ~1;
     L.total = L.vec + DN_NVEC * L.E;
     return L;
@@ -95,8 +96,11 @@ template <typename real>
 struct DenseCtx {
     const IpmArgs<real>& a;
     int tid, lane, N, E, T, GS, ti, tj;
+    int fi, fj;                     // factor_rl1's own thread -> tile map (fj < 0: no work)
     real *Ht, *Lt;
     real *f, *ubar, *ucur, *tl, *tu, *ll, *lu, *cl, *cu, *ua, *usol, *rt, *dR, *tv, *itl, *itu, *ill, *ilu, *fx, *fv;
+    unsigned long long* cbar;       // completion flag of every block column (factor_cols)
+    unsigned fgen;                  // factorisations done so far by this CTA = generation of the flags
 
     // tv = H x  (thread per row; H symmetric, stored as 4x4 tiles of the lower triangle)
     __device__ __forceinline__ void matvec(const real* x)
@@ -122,10 +126,243 @@ struct DenseCtx {
     }
 
     // Lt = chol(K): K = H + diag(dR) (IPM) or H with the inputs flagged in fx replaced by identity rows/columns.
-    // One thread per 4x4 tile, right-looking over block columns; the current panel goes through shared memory and
-    // the next diagonal block is factored while the other tiles take their update.  Diagonal tiles of Lt hold the
-    // INVERSE of their 4x4 factor.  Threads T..T+N-1 carry the right-hand side rt along as one more block row, so
-    // rt leaves as Lam^-1 rt (the forward substitution costs no extra pass).
+    // Diagonal tiles of Lt hold the INVERSE of their 4x4 factor; the right-hand side rt rides along as one more block
+    // row, so rt leaves as Lam^-1 rt (the forward substitution costs no extra pass).
+    //
+    // Left-looking, ONE WARP PER BLOCK COLUMN, no CTA barrier inside (QMPC_DENSE_FACTOR 1, default).  Warp w owns the
+    // block columns w, w + 8, w + 16; lane i of column j carries tile (j + i, j), lane N - j the right-hand-side row.
+    // Column j subtracts the products L(j+i, k) L(j, k)' of every finished column k < j as soon as that column's flag
+    // completes (an mbarrier the producer warp arrives on: release / acquire at CTA scope, waiters suspend in hardware).
+    // Every lane also carries the diagonal tile (j, j) and factors it itself (the 4x4 Cholesky costs a warp the same
+    // whether one lane or all run it), so the lanes substitute their own rows without a broadcast or a warp barrier and
+    // the warp raises the column's flag.  The serial chain per block column is one tile product + the 4x4 Cholesky; the
+    // right-looking variant below (one thread per tile, kept for A/B) pays two CTA barriers per block column on top
+    // with seven of its eight warps waiting (profiles/r02_solver_summary.txt: 57 % of the warp samples at a barrier).
+    __device__ __forceinline__ void factor_cols(const bool fixed)
+    {
+        const int warp = tid >> 5;
+        for (int j = warp; j < N; j += DN_THREADS / 32) {
+            const int rows = N - j;
+            const bool tile = lane > 0 && lane < rows, rhs = lane == rows;
+            const int i = tile ? j + lane : j;
+            // dg: the diagonal tile (j, j), carried REDUNDANTLY by every lane (lower triangle); acc: this lane's own tile
+            real acc[16], dg[16];
+            real kj[4] = {1, 1, 1, 1};
+            {
+                const real* p = Ht + tri(j, j) * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(p + t, dg[t], dg[t + 1]);
+                if (fixed) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) kj[q] = fx[4 * j + q] != real(0) ? real(0) : real(1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) dg[q * 4 + r] *= kj[q] * kj[r];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (kj[q] == real(0)) dg[q * 5] = real(1);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dg[q * 5] += dR[4 * j + q];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc[t] = 0;
+            if (tile) {
+                const real* p = Ht + tri(i, j) * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(p + t, acc[t], acc[t + 1]);
+                if (fixed) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const real ki = fx[4 * i + q] != real(0) ? real(0) : real(1);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[q * 4 + r] *= ki * kj[r];
+                    }
+                }
+            } else if (rhs) {
+                ld2(rt + 4 * j, acc[0], acc[1]); ld2(rt + 4 * j + 2, acc[2], acc[3]);
+            }
+            for (int k = 0; k < j; ++k) {
+                flag_wait(cbar + k, fgen);
+                real lj[16];
+                const real* pj = Lt + tri(j, k) * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r <= q; ++r) {
+                        real s = dg[q * 4 + r];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
+                        dg[q * 4 + r] = s;
+                    }
+                // row q of this lane's left factor: tile (i, k), or the forward-substituted right-hand side of block k
+                const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;
+                const int nq = rhs ? 1 : (tile ? 4 : 0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < nq) {
+                        real l0, l1, l2, l3;
+                        ld2(pi + q * 4, l0, l1); ld2(pi + q * 4 + 2, l2, l3);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            real s = acc[q * 4 + r];
+                            s = fma(-l0, lj[r * 4], s); s = fma(-l1, lj[r * 4 + 1], s);
+                            s = fma(-l2, lj[r * 4 + 2], s); s = fma(-l3, lj[r * 4 + 3], s);
+                            acc[q * 4 + r] = s;
+                        }
+                    }
+                }
+            }
+            // every lane factors the diagonal tile itself: no broadcast, no warp barrier, and the substitution of the
+            // lane's own rows fills the latency gaps of the 4x4 Cholesky's dependent chain
+            Chol4<real> L;
+            L.factor(dg);
+            L.pin();
+            if (tile) {
+                real* o = Lt + tri(i, j) * TS;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    real z[4];
+                    L.fsolve(acc + q * 4, z);
+                    st2(o + q * 4, z[0], z[1]); st2(o + q * 4 + 2, z[2], z[3]);
+                }
+            } else if (rhs) {
+                real y[4];
+                L.fsolve(acc, y);
+                st2(rt + 4 * j, y[0], y[1]); st2(rt + 4 * j + 2, y[2], y[3]);
+            }
+            flag_arrive(cbar + j);
+            if (lane == 0) {            // the inverse of the diagonal factor is only read by solve(), after the closing barrier
+                Inv4<real> Ni;
+                Ni.from(L);
+                Ni.store(Lt + tri(j, j) * TS);
+            }
+        }
+        ++fgen;
+        __syncthreads();
+    }
+
+    // Right-looking, one thread per 4x4 tile, ONE CTA barrier per block column (QMPC_DENSE_FACTOR 2).  A warp-level
+    // fp64 instruction occupies the SMSP's fp64 pipe for two cycles however few lanes are active, so the mapping packs
+    // the active lanes: tiles are numbered column-major (see the kernel prologue).  Every thread of
+    // block column c (its tiles and the right-hand-side thread of block c) also carries the diagonal tile (c, c): the
+    // update with column K subtracts L(c,K) L(c,K)' from it - the thread has loaded L(c,K) anyway - so when column c
+    // becomes current each of its threads factors the diagonal tile itself and substitutes its own rows at once.  The
+    // separate panel phase of the variant below (a second barrier per block column, one thread factoring while 255 wait)
+    // is gone; the price is 40 more FMAs per tile update.
+    __device__ __forceinline__ void factor_rl1(const bool fixed)
+    {
+        // thread -> (row fi, column fj) of the factorisation, COLUMN-major: the N - c tiles of block column c and its
+        // right-hand-side thread (fi == N) are consecutive threads, so the threads that factor the current column sit
+        // in one or two warps and the warps whose columns are finished drop out of the updates entirely
+        const bool work = fj >= 0, rhs = work && fi == N, tile = work && !rhs;
+        const int col = work ? fj : 0, ti = tile ? fi : 0;
+        const bool below = tile && fi > fj;
+        const int tix = tri(ti, col);       // tile index in Ht / Lt
+        real acc[16], dg[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { acc[t] = 0; dg[t] = 0; }
+        if (work) {
+            real kj[4] = {1, 1, 1, 1};
+            const real* p = Ht + tri(col, col) * TS;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) ld2(p + t, dg[t], dg[t + 1]);
+            if (fixed) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) kj[q] = fx[4 * col + q] != real(0) ? real(0) : real(1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) dg[q * 4 + r] *= kj[q] * kj[r];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (kj[q] == real(0)) dg[q * 5] = real(1);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dg[q * 5] += dR[4 * col + q];
+            }
+            if (below) {
+                const real* pa = Ht + tix * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(pa + t, acc[t], acc[t + 1]);
+                if (fixed) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const real ki = fx[4 * ti + q] != real(0) ? real(0) : real(1);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[q * 4 + r] *= ki * kj[r];
+                    }
+                }
+            } else if (rhs) {
+                ld2(rt + 4 * col, acc[0], acc[1]); ld2(rt + 4 * col + 2, acc[2], acc[3]);
+            }
+        }
+        for (int K = 0; K < N; ++K) {
+            const bool current = work && col == K;
+            Chol4<real> L;
+            if (current) {
+                L.factor(dg);
+                L.pin();
+                if (below) {
+                    real* o = Lt + tix * TS;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        real z[4];
+                        L.fsolve(acc + q * 4, z);
+                        st2(o + q * 4, z[0], z[1]); st2(o + q * 4 + 2, z[2], z[3]);
+                    }
+                } else if (rhs) {
+                    real y[4];
+                    L.fsolve(acc, y);
+                    st2(rt + 4 * K, y[0], y[1]); st2(rt + 4 * K + 2, y[2], y[3]);
+                }
+            }
+            __syncthreads();
+            if (current && tile && !below) {    // the diagonal thread: the inverse is only read by solve(), after the last barrier
+                Inv4<real> Ni;
+                Ni.from(L);
+                Ni.store(Lt + tix * TS);
+            }
+            if (work && col > K) {
+                real lj[16];
+                const real* pj = Lt + tri(col, K) * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r <= q; ++r) {
+                        real s = dg[q * 4 + r];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
+                        dg[q * 4 + r] = s;
+                    }
+                const real* pi = rhs ? rt + 4 * K : Lt + tri(ti, K) * TS;
+                const int nq = rhs ? 1 : (below ? 4 : 0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < nq) {
+                        real l0, l1, l2, l3;
+                        ld2(pi + q * 4, l0, l1); ld2(pi + q * 4 + 2, l2, l3);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            real s = acc[q * 4 + r];
+                            s = fma(-l0, lj[r * 4], s); s = fma(-l1, lj[r * 4 + 1], s);
+                            s = fma(-l2, lj[r * 4 + 2], s); s = fma(-l3, lj[r * 4 + 3], s);
+                            acc[q * 4 + r] = s;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();        // the last diagonal inverse is visible to solve()
+    }
+
+    // Right-looking variant (QMPC_DENSE_FACTOR 0), same result: one thread per 4x4 tile; the current panel goes through
+    // shared memory and the next diagonal block is factored while the other tiles take their update (two CTA barriers
+    // per block column).  Threads T..T+N-1 carry the right-hand side.
     __device__ __forceinline__ void factor(const bool fixed)
     {
         real acc[16];
@@ -291,6 +528,9 @@ struct DenseCtx {
 // element loop of warp 0: e = lane, lane + 32, lane + 64 (E <= 96), unrolled so the three elements overlap
 #define DN_FOR_E(e) _Pragma("unroll") for (int e##_m = 0; e##_m < 3; ++e##_m) for (int e = lane + 32 * e##_m; e < E; e = E)
 
+#ifndef QMPC_DENSE_FACTOR
+#define QMPC_DENSE_FACTOR 0         // 2: tile per thread, one barrier per block column (factor_rl1); 1: column per warp, flags (factor_cols); 0: two barriers (factor)
+#endif
 #ifndef QMPC_DENSE_MIN_CTAS
 #define QMPC_DENSE_MIN_CTAS 2       // register budget: 2 -> 128 registers per thread
 #endif
@@ -329,10 +569,19 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
         c.ti = i; c.tj = tid - i * (i + 1) / 2;
     }
     const int ti = c.ti, tj = c.tj;
+    {   // column-major map of the factorisation: column cc owns threads S(cc) .. S(cc) + N - cc (the last one = right-hand side)
+        int cc = 0, start = 0;
+        while (cc < N && start + (N - cc + 1) <= tid) { start += N - cc + 1; ++cc; }
+        c.fj = cc < N ? cc : -1;
+        c.fi = cc + (tid - start);
+    }
     const int count = da.hard_list ? *da.hard_count : a.B;
     const real lb = a.lb, ub = a.ub;
     if (tid < NX) { sq[tid] = sqrt(a.Qd[tid]); sq[16 + tid] = sqrt(a.QNd[tid]); }
     if (tid == 0) mbar_init(mbar, 1);
+    c.cbar = reinterpret_cast<unsigned long long*>(sm + lay.cbar);
+    c.fgen = 0;
+    if (tid < N) flag_init(c.cbar + tid);
     const unsigned tile_bytes = (unsigned)(N * WT * sizeof(real));
     // condensing roles: thread t < T accumulates tile t of H; thread DN_THREADS-1-c carries impulse-response column c
     // (c < E) or the free response (c == E) through the stages - the LAST warps, whose tiles join the sum last, so the
@@ -523,7 +772,13 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     }
                 }
                 __syncthreads();
+#if QMPC_DENSE_FACTOR == 2
+                c.factor_rl1(trip == T_FIXED);
+#elif QMPC_DENSE_FACTOR == 1
+                c.factor_cols(trip == T_FIXED);
+#else
                 c.factor(trip == T_FIXED);
+#endif
             }
             DPROF(2);
             // (3) warp 0: solves, step logic, next trip
