@@ -136,6 +136,8 @@ __device__ __forceinline__ void flag_init(unsigned long long* bar)
 {
 #ifdef QMPC_EMU
     __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST);
+#elif defined(QMPC_FLAG_SPIN)
+    *reinterpret_cast<volatile unsigned*>(bar) = 0u;
 #else
     mbar_init(bar, 32);
 #endif
@@ -144,6 +146,8 @@ __device__ __forceinline__ void flag_arrive(unsigned long long* bar)
 {
 #ifdef QMPC_EMU
     __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST);
+#elif defined(QMPC_FLAG_SPIN)       // A/B variant: a generation counter polled with acquire loads (every lane adds 1)
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
 #else
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 #endif
@@ -152,6 +156,9 @@ __device__ __forceinline__ void flag_wait(unsigned long long* bar, unsigned gene
 {
 #ifdef QMPC_EMU
     while (__atomic_load_n(bar, __ATOMIC_ACQUIRE) < 32ull * (generation + 1ull)) std::this_thread::yield();
+#elif defined(QMPC_FLAG_SPIN)
+    unsigned v;
+    do { asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(bar)) : "memory"); } while (v < 32u * (generation + 1u));
 #else
     mbar_wait(bar, generation & 1u);
 #endif
@@ -165,6 +172,28 @@ template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return 1.0
 template <> __device__ __forceinline__ double rrsqrt<double>(double x) { return rsqrt(x); }
 template <> __device__ __forceinline__ float rrsqrt<float>(float x) { return 1.0f / sqrtf(x); }
 #endif
+
+#ifndef QMPC_RSQRT_NOBRANCH
+#define QMPC_RSQRT_NOBRANCH 1       // the 4x4 Cholesky of both solver kernels uses rsqrt_nobranch (0: the library rsqrt, A/B)
+#endif
+// Branch-free 1/sqrt(x) in double: hardware approximation (2^-22) + two Newton steps -> ~1 ulp.  The library rsqrt() wraps
+// the same approximation in a test-and-call for denormal / huge arguments, and that branch ends the basic block: the
+// scheduler can then not move independent work into the latency of a chain of rsqrts (the dense kernel's 4x4 Cholesky).
+// x <= 0, NaN -> NaN / inf as the library; denormal x is flushed to 0 -> inf (the callers treat non-finite as breakdown).
+__device__ __forceinline__ double rsqrt_nobranch(double x)
+{
+#ifdef QMPC_EMU
+    return 1.0 / sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+#endif
+}
 
 template <typename real> __device__ __forceinline__ bool rfinite(real x) { return x - x == real(0); }
 

@@ -328,16 +328,21 @@ __device__ __forceinline__ void st2(real* p, real a, real b)
 template <typename real>
 struct Chol4 {   // Lam = chol(M_uu) with reciprocal diagonal; inputs / outputs of any floating type, arithmetic in `real`
     real l10, l20, l21, l30, l31, l32, i0, i1, i2, i3;
-    template <typename T>
+    // NOBRANCH (double only): reciprocal square roots without the library's special-case branch (common.cuh rsqrt_nobranch)
+    template <typename T, bool NOBRANCH = false>
     __device__ __forceinline__ void factor(const T* M /* 4x4 row-major, lower used */)
     {
-        i0 = rrsqrt<real>(real(M[0]));
+        auto rs = [](real x) -> real {
+            if constexpr (NOBRANCH && sizeof(real) == 8) return real(rsqrt_nobranch(double(x)));
+            else return rrsqrt<real>(x);
+        };
+        i0 = rs(real(M[0]));
         l10 = real(M[4]) * i0; l20 = real(M[8]) * i0; l30 = real(M[12]) * i0;
-        i1 = rrsqrt<real>(real(M[5]) - l10 * l10);
+        i1 = rs(real(M[5]) - l10 * l10);
         l21 = (real(M[9]) - l20 * l10) * i1; l31 = (real(M[13]) - l30 * l10) * i1;
-        i2 = rrsqrt<real>(real(M[10]) - l20 * l20 - l21 * l21);
+        i2 = rs(real(M[10]) - l20 * l20 - l21 * l21);
         l32 = (real(M[14]) - l30 * l20 - l31 * l21) * i2;
-        i3 = rrsqrt<real>(real(M[15]) - l30 * l30 - l31 * l31 - l32 * l32);
+        i3 = rs(real(M[15]) - l30 * l30 - l31 * l31 - l32 * l32);
     }
     // Keeps the factorisation where it is written: without it the compiler sinks factor() into each of the divergent
     // branches that use the result (tile rows / right-hand side / diagonal), and a warp then runs the 4x4 Cholesky's
@@ -626,7 +631,11 @@ struct WarpCtx {
                 real Muu[16];
 #pragma unroll
                 for (int t = 0; t < 16; t += 2) ld2(cs + t, Muu[t], Muu[t + 1]);
+#if QMPC_RSQRT_NOBRANCH
+                L.template factor<real, true>(Muu);
+#else
                 L.factor(Muu);
+#endif
                 real gu[4];
                 ld2(cs + 28, gu[0], gu[1]); ld2(cs + 30, gu[2], gu[3]);
                 L.fsolve(gu, lg);

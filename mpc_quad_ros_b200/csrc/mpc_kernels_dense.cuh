@@ -12,6 +12,14 @@
 #pragma once
 #include "mpc_kernels.cuh"
 
+// build-time variants (A/B): see the functions they select
+#ifndef QMPC_DENSE_FACTOR
+#define QMPC_DENSE_FACTOR 0         // 2: tile per thread, one barrier per block column (factor_rl1); 1: column per warp, flags (factor_cols); 0: two barriers (factor)
+#endif
+#ifndef QMPC_DENSE_MATVEC2
+#define QMPC_DENSE_MATVEC2 0        // 1: two threads per row of H x (measured slower under load: -2.7 %, profiles/r02_policy_ab.txt)
+#endif
+
 namespace qmpc {
 
 constexpr int DN_THREADS = 256;
@@ -93,54 +101,25 @@ struct Inv4 {
 };
 
 template <typename real>
-struct DenseCtx {
-    const IpmArgs<real>& a;
-    int tid, lane, N, E, T, GS, ti, tj;
-    int fi, fj;                     // factor_rl1's own thread -> tile map (fj < 0: no work)
-    real *Ht, *Lt;
-    real *f, *ubar, *ucur, *tl, *tu, *ll, *lu, *cl, *cu, *ua, *usol, *rt, *dR, *tv, *itl, *itu, *ill, *ilu, *fx, *fv;
-    unsigned long long* cbar;       // completion flag of every block column (factor_cols)
-    unsigned fgen;                  // factorisations done so far by this CTA = generation of the flags
-
-    // tv = H x  (thread per row; H symmetric, stored as 4x4 tiles of the lower triangle)
-    __device__ __forceinline__ void matvec(const real* x)
-    {
-        if (tid < E) {
-            const int I = tid >> 2, ar = tid & 3;
-            real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int J = 0; J <= I; ++J) {
-                const real* p = Ht + tri(I, J) * TS + ar * 4;
-                real h0, h1, h2, h3, x0, x1, x2, x3;
-                ld2(p, h0, h1); ld2(p + 2, h2, h3);
-                ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
-                s0 = fma(h0, x0, s0); s1 = fma(h1, x1, s1); s2 = fma(h2, x2, s2); s3 = fma(h3, x3, s3);
-            }
-            for (int J = I + 1; J < N; ++J) {
-                const real* p = Ht + tri(J, I) * TS + ar;
-                real x0, x1, x2, x3;
-                ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
-                s0 = fma(p[0], x0, s0); s1 = fma(p[4], x1, s1); s2 = fma(p[8], x2, s2); s3 = fma(p[12], x3, s3);
-            }
-            tv[tid] = (s0 + s1) + (s2 + s3);
-        }
-    }
-
-    // Lt = chol(K): K = H + diag(dR) (IPM) or H with the inputs flagged in fx replaced by identity rows/columns.
-    // Diagonal tiles of Lt hold the INVERSE of their 4x4 factor; the right-hand side rt rides along as one more block
-    // row, so rt leaves as Lam^-1 rt (the forward substitution costs no extra pass).
-    //
-    // Left-looking, ONE WARP PER BLOCK COLUMN, no CTA barrier inside (QMPC_DENSE_FACTOR 1, default).  Warp w owns the
-    // block columns w, w + 8, w + 16; lane i of column j carries tile (j + i, j), lane N - j the right-hand-side row.
-    // Column j subtracts the products L(j+i, k) L(j, k)' of every finished column k < j as soon as that column's flag
-    // completes (an mbarrier the producer warp arrives on: release / acquire at CTA scope, waiters suspend in hardware).
-    // Every lane also carries the diagonal tile (j, j) and factors it itself (the 4x4 Cholesky costs a warp the same
-    // whether one lane or all run it), so the lanes substitute their own rows without a broadcast or a warp barrier and
-    // the warp raises the column's flag.  The serial chain per block column is one tile product + the 4x4 Cholesky; the
-    // right-looking variant below (one thread per tile, kept for A/B) pays two CTA barriers per block column on top
-    // with seven of its eight warps waiting (profiles/r02_solver_summary.txt: 57 % of the warp samples at a barrier).
-    __device__ __forceinline__ void factor_cols(const bool fixed)
-    {
-        const int warp = tid >> 5;
+#ifdef QMPC_FCOLS_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void factor_cols_fn(const int oHt, const int oLt, const int oRt, const int oFx, const int oDR, const int oCbar,
+                                            const unsigned fgen, const int N, const int tid, const bool fixed)
+{
+        // the arrays arrive as offsets into the CTA's dynamic shared memory and are rebuilt from the shared symbol here:
+        // pointer arguments of a non-inlined function are generic, and every access would be a generic LD / ST
+        QMPC_DYN_SMEM(smem_raw);
+        real* const sm = reinterpret_cast<real*>(smem_raw);
+        const real* const Ht = sm + oHt;
+        real* const Lt = sm + oLt;
+        real* const rt = sm + oRt;
+        const real* const fx = sm + oFx;
+        const real* const dR = sm + oDR;
+        unsigned long long* const cbar = reinterpret_cast<unsigned long long*>(sm + oCbar);
+        const int warp = tid >> 5, lane = tid & 31;
         for (int j = warp; j < N; j += DN_THREADS / 32) {
             const int rows = N - j;
             const bool tile = lane > 0 && lane < rows, rhs = lane == rows;
@@ -183,7 +162,7 @@ struct DenseCtx {
             } else if (rhs) {
                 ld2(rt + 4 * j, acc[0], acc[1]); ld2(rt + 4 * j + 2, acc[2], acc[3]);
             }
-            for (int k = 0; k < j; ++k) {
+            for (int k = 0; k < j - 1; ++k) {       // look-ahead: columns finished long ago
                 flag_wait(cbar + k, fgen);
                 real lj[16];
                 const real* pj = Lt + tri(j, k) * TS;
@@ -216,23 +195,52 @@ struct DenseCtx {
                     }
                 }
             }
-            // every lane factors the diagonal tile itself: no broadcast, no warp barrier, and the substitution of the
-            // lane's own rows fills the latency gaps of the 4x4 Cholesky's dependent chain
+            // The column that has just finished (k = j - 1) is the serial chain of the whole factorisation: its product, the
+            // 4x4 Cholesky of the diagonal tile and the substitution of this lane's rows form ONE basic block (no branch:
+            // idle lanes compute on valid dummy addresses, the reciprocal square roots are branch-free), so the scheduler
+            // moves the 64 FMAs of the lane's own tile into the latency of the Cholesky's dependent chain.
+            if (j > 0) {
+                const int k = j - 1;
+                flag_wait(cbar + k, fgen);
+                real lj[16];
+                const real* pj = Lt + tri(j, k) * TS;
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
+                const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;      // i == j for lanes without a tile: a valid address
+                real li[16];
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(pi + t, li[t], li[t + 1]);   // (right-hand side lane: rows 1..3 read on into rt; unused)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r <= q; ++r) {
+                        real s = dg[q * 4 + r];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
+                        dg[q * 4 + r] = s;
+                    }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        real s = acc[q * 4 + r];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s = fma(-li[q * 4 + c], lj[r * 4 + c], s);
+                        acc[q * 4 + r] = s;
+                    }
+            }
+            // every lane factors the diagonal tile itself: no broadcast, no warp barrier
             Chol4<real> L;
-            L.factor(dg);
-            L.pin();
+            L.template factor<real, true>(dg);
+            real z[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) L.fsolve(acc + q * 4, z + q * 4);
             if (tile) {
                 real* o = Lt + tri(i, j) * TS;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    real z[4];
-                    L.fsolve(acc + q * 4, z);
-                    st2(o + q * 4, z[0], z[1]); st2(o + q * 4 + 2, z[2], z[3]);
-                }
+                for (int t = 0; t < 16; t += 2) st2(o + t, z[t], z[t + 1]);
             } else if (rhs) {
-                real y[4];
-                L.fsolve(acc, y);
-                st2(rt + 4 * j, y[0], y[1]); st2(rt + 4 * j + 2, y[2], y[3]);
+                st2(rt + 4 * j, z[0], z[1]); st2(rt + 4 * j + 2, z[2], z[3]);
             }
             flag_arrive(cbar + j);
             if (lane == 0) {            // the inverse of the diagonal factor is only read by solve(), after the closing barrier
@@ -241,8 +249,80 @@ struct DenseCtx {
                 Ni.store(Lt + tri(j, j) * TS);
             }
         }
-        ++fgen;
         __syncthreads();
+}
+
+
+template <typename real>
+struct DenseCtx {
+    const IpmArgs<real>& a;
+    int tid, lane, N, E, T, GS, ti, tj;
+    int fi, fj;                     // factor_rl1's own thread -> tile map (fj < 0: no work)
+    real *Ht, *Lt;
+    real *f, *ubar, *ucur, *tl, *tu, *ll, *lu, *cl, *cu, *ua, *usol, *rt, *dR, *tv, *itl, *itu, *ill, *ilu, *fx, *fv;
+    real* smbase;                   // start of the CTA's dynamic shared memory
+    unsigned long long* cbar;       // completion flag of every block column (factor_cols)
+    unsigned fgen;                  // factorisations done so far by this CTA = generation of the flags
+
+    // tv = H x  (H symmetric, stored as 4x4 tiles of the lower triangle).  Two threads per row - the even and the odd block
+    // columns - combined with one shuffle; whole warps take part (rows past the end are computed redundantly, not stored).
+    __device__ __forceinline__ void matvec(const real* x)
+    {
+#if QMPC_DENSE_MATVEC2
+        const int nthr = (2 * E + 31) & ~31;
+        if (tid < nthr) {
+            const int row = (tid >> 1) < E ? (tid >> 1) : E - 1, half = tid & 1;
+            const int I = row >> 2, ar = row & 3;
+            real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 2
+            for (int J = half; J <= I; J += 2) {
+                const real* p = Ht + tri(I, J) * TS + ar * 4;
+                real h0, h1, h2, h3, x0, x1, x2, x3;
+                ld2(p, h0, h1); ld2(p + 2, h2, h3);
+                ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
+                s0 = fma(h0, x0, s0); s1 = fma(h1, x1, s1); s2 = fma(h2, x2, s2); s3 = fma(h3, x3, s3);
+            }
+#pragma unroll 2
+            for (int J = I + 1 + ((I + 1 + half) & 1); J < N; J += 2) {       // first J > I with J == half (mod 2)
+                const real* p = Ht + tri(J, I) * TS + ar;
+                real x0, x1, x2, x3;
+                ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
+                s0 = fma(p[0], x0, s0); s1 = fma(p[4], x1, s1); s2 = fma(p[8], x2, s2); s3 = fma(p[12], x3, s3);
+            }
+            real s = (s0 + s1) + (s2 + s3);
+            s += __shfl_xor_sync(FULL, s, 1);
+            if (half == 0 && (tid >> 1) < E) tv[row] = s;
+        }
+#else
+        if (tid < E) {
+            const int I = tid >> 2, ar = tid & 3;
+            real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int J = 0; J <= I; ++J) {
+                const real* p = Ht + tri(I, J) * TS + ar * 4;
+                real h0, h1, h2, h3, x0, x1, x2, x3;
+                ld2(p, h0, h1); ld2(p + 2, h2, h3);
+                ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
+                s0 = fma(h0, x0, s0); s1 = fma(h1, x1, s1); s2 = fma(h2, x2, s2); s3 = fma(h3, x3, s3);
+            }
+            for (int J = I + 1; J < N; ++J) {
+                const real* p = Ht + tri(J, I) * TS + ar;
+                real x0, x1, x2, x3;
+                ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
+                s0 = fma(p[0], x0, s0); s1 = fma(p[4], x1, s1); s2 = fma(p[8], x2, s2); s3 = fma(p[12], x3, s3);
+            }
+            tv[tid] = (s0 + s1) + (s2 + s3);
+        }
+#endif
+    }
+
+    // NOT inlined on purpose: inside the kernel the register allocator has the solver's ~25 vector pointers live across the
+    // call and schedules this loop 60 % slower than the same code compiled on its own (38.7 k against 23.6 k cycles per
+    // factorisation, scripts/ubench/factor.cu)
+    __device__ __forceinline__ void factor_cols(const bool fixed)
+    {
+        factor_cols_fn<real>(int(Ht - smbase), int(Lt - smbase), int(rt - smbase), int(fx - smbase), int(dR - smbase),
+                             int(reinterpret_cast<real*>(cbar) - smbase), fgen, N, tid, fixed);
+        ++fgen;
     }
 
     // Right-looking, one thread per 4x4 tile, ONE CTA barrier per block column (QMPC_DENSE_FACTOR 2).  A warp-level
@@ -397,7 +477,11 @@ struct DenseCtx {
         }
         if (tid == 0) {
             Chol4<real> L;
+#if QMPC_RSQRT_NOBRANCH
+            L.template factor<real, true>(acc);
+#else
             L.factor(acc);
+#endif
             Inv4<real> Ni;
             Ni.from(L);
             Ni.store(Lt);
@@ -442,7 +526,11 @@ struct DenseCtx {
                     }
                 if (ti == K + 1 && tj == K + 1) {
                     Chol4<real> L;
-                    L.factor(acc);
+        #if QMPC_RSQRT_NOBRANCH
+            L.template factor<real, true>(acc);
+#else
+            L.factor(acc);
+#endif
                     Inv4<real> Ni;
                     Ni.from(L);
                     Ni.store(Lt + tid * TS);
@@ -528,9 +616,6 @@ struct DenseCtx {
 // element loop of warp 0: e = lane, lane + 32, lane + 64 (E <= 96), unrolled so the three elements overlap
 #define DN_FOR_E(e) _Pragma("unroll") for (int e##_m = 0; e##_m < 3; ++e##_m) for (int e = lane + 32 * e##_m; e < E; e = E)
 
-#ifndef QMPC_DENSE_FACTOR
-#define QMPC_DENSE_FACTOR 0         // 2: tile per thread, one barrier per block column (factor_rl1); 1: column per warp, flags (factor_cols); 0: two barriers (factor)
-#endif
 #ifndef QMPC_DENSE_MIN_CTAS
 #define QMPC_DENSE_MIN_CTAS 2       // register budget: 2 -> 128 registers per thread
 #endif
@@ -580,6 +665,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
     if (tid < NX) { sq[tid] = sqrt(a.Qd[tid]); sq[16 + tid] = sqrt(a.QNd[tid]); }
     if (tid == 0) mbar_init(mbar, 1);
     c.cbar = reinterpret_cast<unsigned long long*>(sm + lay.cbar);
+    c.smbase = sm;
     c.fgen = 0;
     if (tid < N) flag_init(c.cbar + tid);
     const unsigned tile_bytes = (unsigned)(N * WT * sizeof(real));
@@ -772,6 +858,20 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     }
                 }
                 __syncthreads();
+#ifdef QMPC_FACTOR_TWICE                 // experiment: is the first call slower than a repeat (cold code / cold data)?
+                if (trip == T_FIXED) {
+                    for (int e = tid; e < E; e += DN_THREADS) c.tv[e] = c.rt[e];
+                    __syncthreads();
+#if QMPC_DENSE_FACTOR == 1
+                    c.factor_cols(true);
+#else
+                    c.factor(true);
+#endif
+                    for (int e = tid; e < E; e += DN_THREADS) c.rt[e] = c.tv[e];
+                    __syncthreads();
+                }
+#endif
+                DPROF(7);
 #if QMPC_DENSE_FACTOR == 2
                 c.factor_rl1(trip == T_FIXED);
 #elif QMPC_DENSE_FACTOR == 1
@@ -797,6 +897,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     next = T_PRED;
                 } else if (trip == T_FIXED) {
                     c.solve(c.rt, c.usol, true);
+                    DPROF(8);
                     next = T_ADJ;
                 } else if (trip == T_ADJ) {
                     ++rounds;
@@ -1025,8 +1126,8 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
         if (a.timeline && tid == 0) a.timeline[2 * ocp + 1] = global_ns();
 #ifdef QMPC_DENSE_PROF
         if (tid == 0 && item < 3)
-            printf("dense ocp %d it %d rounds %d | cycles: condense %lld | matvec %lld (%d) | factor %lld (%d) | solves %lld (%d) | logic %lld | rollout %lld | loop-top %lld | total %lld\n",
-                   ocp, it, rounds, pf_acc[0], pf_acc[1], pf_n[1], pf_acc[2], pf_n[2], pf_acc[3], pf_n[3], pf_acc[6], pf_acc[4], pf_acc[5], clock64() - pf_t0);
+            printf("dense ocp %d it %d rounds %d | cycles: condense %lld | matvec %lld (%d) | factor %lld (%d) | rhs %lld (%d) | solves %lld (%d) | back-substitution of a round %lld (%d) | logic %lld | rollout %lld | loop-top %lld | total %lld\n",
+                   ocp, it, rounds, pf_acc[0], pf_acc[1], pf_n[1], pf_acc[2], pf_n[2], pf_acc[7], pf_n[7], pf_acc[3], pf_n[3], pf_acc[8], pf_n[8], pf_acc[6], pf_acc[4], pf_acc[5], clock64() - pf_t0);
 #endif
         __syncthreads();
         item = ctl[qslot];

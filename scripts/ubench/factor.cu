@@ -16,7 +16,7 @@ template <int V> __global__ void __launch_bounds__(256, 2) k(const double* Hin, 
     c.Ht = sm + lay.Ht; c.Lt = sm + lay.Lt;
     double* v = sm + lay.vec;
     c.rt = v + 11 * c.E; c.dR = v + 12 * c.E; c.cl = v + 7 * c.E; c.fx = c.cl;
-    c.cbar = reinterpret_cast<unsigned long long*>(sm + lay.cbar); c.fgen = 0;
+    c.cbar = reinterpret_cast<unsigned long long*>(sm + lay.cbar); c.fgen = 0; c.smbase = sm;
     if (tid < N) flag_init(c.cbar + tid);
     { int i = 0; while ((i + 1) * (i + 2) / 2 <= tid) ++i; c.ti = i; c.tj = tid - i * (i + 1) / 2; }
     { int cc = 0, start = 0; while (cc < N && start + (N - cc + 1) <= tid) { start += N - cc + 1; ++cc; } c.fj = cc < N ? cc : -1; c.fi = cc + (tid - start); }

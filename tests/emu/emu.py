@@ -10,7 +10,9 @@ from mpc_quad_ros_b200._capi import QmpcConfig
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBS = {}
 # build flavours of the emulated kernels: name -> (extra compiler defines, tile row stride)
-FLAVOURS = {"": ([], 18), "noring": (["-DQMPC_RING=0", "-DQMPC_WR=16"], 16), "trace": (["-DQMPC_EMU_TRACE"], 18)}
+FLAVOURS = {"": ([], 18), "noring": (["-DQMPC_RING=0", "-DQMPC_WR=16"], 16), "trace": (["-DQMPC_EMU_TRACE"], 18),
+            # the dense kernel's other Cholesky variants (QMPC_DENSE_FACTOR in mpc_kernels_dense.cuh)
+            "factor0": (["-DQMPC_DENSE_FACTOR=0"], 18), "factor1": (["-DQMPC_DENSE_FACTOR=1"], 18), "factor2": (["-DQMPC_DENSE_FACTOR=2"], 18)}
 
 
 def lib(flavour=""):

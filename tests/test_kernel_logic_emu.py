@@ -186,6 +186,32 @@ def test_emulated_build_without_tile_ring_matches_oracle(variant):
     assert (r2["status"] == 0).all() and u_rel(u2, uo2) < TOL[variant] and x_rel(x2, xo2) < TOL[variant]
 
 
+@pytest.mark.parametrize("flavour", ["factor0", "factor1", "factor2"])
+def test_emulated_dense_kernel_cholesky_variants(flavour):
+    """the dense kernel's three blocked Cholesky variants (two CTA barriers per block column / one warp per block column with
+    completion flags between the warps / one barrier per block column with a redundant diagonal tile) land on the oracle's
+    minimiser: cold solve (IPM + rounds, factorisations with dR) and warm-started second solve (pinned rounds), N = 20 and an
+    odd horizon whose last block column sits alone in its warp"""
+    for N in (20, 7):
+        B = 3
+        dt = 1.0 / N
+        quad = orc.quad_hummingbird()
+        gp = make_gp(20)
+        sc = random_ocp_batch(B, N, dt, quad, gp, seed=5, amp_choices=(8.0, 2.0))
+        cfg, keep = emu.make_config(B, N, 1.0, quad, orc.W_DIAG, orc.WE_DIAG, gp.X, gp.theta)
+        xo, uo, _, _ = oracle_solve_batch(sc, quad, dt, N, gp)
+        xe, ue = sc["xit"].copy(), sc["uit"].copy()
+        r1 = emu.solve(cfg, sc["x0"], sc["yref"], sc["yref_e"], sc["alpha"], xe, ue, variant=2, flavour=flavour)
+        assert (r1["status"] == 0).all() and u_rel(ue, uo) < TOL[2] and x_rel(xe, xo) < TOL[2]
+        sc2 = dict(sc)
+        sc2["x0"] = sc["x0"] + 0.05 * np.random.default_rng(2).standard_normal(sc["x0"].shape)
+        sc2["xit"], sc2["uit"] = xe.copy(), ue.copy()
+        xo2, uo2, _, _ = oracle_solve_batch(sc2, quad, dt, N, gp)
+        x2, u2 = xe.copy(), ue.copy()
+        r2 = emu.solve(cfg, sc2["x0"], sc["yref"], sc["yref_e"], sc["alpha"], x2, u2, act=r1["act"].copy(), variant=2, flavour=flavour)
+        assert (r2["status"] == 0).all() and u_rel(u2, uo2) < TOL[2] and x_rel(x2, xo2) < TOL[2]
+
+
 @pytest.mark.parametrize("layout", ["equispaced", "equispaced_forced_general", "scattered", "narrow_kernel", "velocities_off_grid"])
 def test_emulated_gp_basis_point_layouts(layout, monkeypatch):
     """K1's GP term: an equispaced axis (linspace) is evaluated with three exps and a recurrence that starts at the basis
