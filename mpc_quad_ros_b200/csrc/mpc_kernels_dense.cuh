@@ -14,7 +14,10 @@
 
 // build-time variants (A/B): see the functions they select
 #ifndef QMPC_DENSE_FACTOR
-#define QMPC_DENSE_FACTOR 0         // 2: tile per thread, one barrier per block column (factor_rl1); 1: column per warp, flags (factor_cols); 0: two barriers (factor)
+#define QMPC_DENSE_FACTOR 1         // 2: tile per thread, one barrier per block column (factor_rl1); 1: column per warp, flags (factor_cols); 0: two barriers (factor)
+#endif
+#ifndef QMPC_DENSE_SCALED_SOLVE
+#define QMPC_DENSE_SCALED_SOLVE 1   // triangular sweeps on tiles pre-scaled by their column's diagonal inverse (scale_for_solves); 0: plain sweeps
 #endif
 #ifndef QMPC_DENSE_MATVEC2
 #define QMPC_DENSE_MATVEC2 0        // 1: two threads per row of H x (measured slower under load: -2.7 %, profiles/r02_policy_ab.txt)
@@ -548,6 +551,81 @@ struct DenseCtx {
         }
     }
 
+#if QMPC_DENSE_SCALED_SOLVE
+    // After the factorisation (all threads): every off-diagonal tile L(i,j) becomes V(i,j) = L(i,j) Lam_j^-1, scaled by the
+    // inverse of its COLUMN's diagonal factor.  Both triangular sweeps then run on the pre-scaled residuals:
+    //   forward   s_J = r_J - sum_{I<J} V(J,I) s_I,            y_J = Lam_J^-1 s_J   once, at the end
+    //   backward  x_K = Lam_K^-T y_K - sum_{I>K} V(I,K)' x_I   (the first term once, at the start)
+    // so a step of the serial chain is one shuffle of four values and one 4x4 product; the product with the diagonal
+    // inverse (16 more dependent fp64 operations per step, issued by one warp) is off the chain.  8.2 k -> see DESIGN.
+    __device__ __forceinline__ void scale_for_solves()
+    {
+        if (tid < T && ti > tj) {
+            Inv4<real> Ni;
+            Ni.load(Lt + tri(tj, tj) * TS);
+            real* p = Lt + tid * TS;
+            real l[16], z[16];
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) ld2(p + t, l[t], l[t + 1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Ni.mulT(l + q * 4, z + q * 4);      // row q of L Lam^-1
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) st2(p + t, z[t], z[t + 1]);
+        }
+        __syncthreads();
+    }
+
+    // warp 0, lane I < N owns block row I: dst = K^-1 rhs with the scaled factor in Lt; fwd_done: rhs already holds Lam^-1 rhs
+    __device__ __forceinline__ void solve(const real* rhs, real* dst, const bool fwd_done)
+    {
+        real r4[4] = {0, 0, 0, 0};
+        const int me = lane < N ? lane : N - 1;         // lanes past the last block row compute on row N-1 and store nothing
+        ld2(rhs + 4 * me, r4[0], r4[1]); ld2(rhs + 4 * me + 2, r4[2], r4[3]);
+        Inv4<real> Nme;
+        Nme.load(Lt + tri(me, me) * TS);
+        if (!fwd_done) {
+            for (int K = 0; K < N - 1; ++K) {
+                const real* p = Lt + tri(me > K ? me : K + 1, K) * TS;       // a valid tile for every lane
+                real l[16], sk[4];
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) ld2(p + t, l[t], l[t + 1]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sk[q] = __shfl_sync(FULL, r4[q], K);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const real upd = r4[q] - ((l[q * 4] * sk[0] + l[q * 4 + 1] * sk[1]) + (l[q * 4 + 2] * sk[2] + l[q * 4 + 3] * sk[3]));
+                    r4[q] = me > K ? upd : r4[q];
+                }
+            }
+            real y[4];
+            Nme.mul(r4, y);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r4[q] = y[q];
+        }
+        {
+            real x[4];
+            Nme.mulT(r4, x);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r4[q] = x[q];
+        }
+        for (int K = N - 1; K > 0; --K) {
+            const real* p = Lt + tri(K, me < K ? me : K - 1) * TS;
+            real l[16], xk[4];
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) ld2(p + t, l[t], l[t + 1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xk[q] = __shfl_sync(FULL, r4[q], K);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const real upd = r4[c] - ((l[c] * xk[0] + l[4 + c] * xk[1]) + (l[8 + c] * xk[2] + l[12 + c] * xk[3]));
+                r4[c] = me < K ? upd : r4[c];
+            }
+        }
+        if (lane < N) { st2(dst + 4 * lane, r4[0], r4[1]); st2(dst + 4 * lane + 2, r4[2], r4[3]); }
+        __syncwarp();
+    }
+#else
+    __device__ __forceinline__ void scale_for_solves() {}
     // warp 0, lane I < N owns block row I: dst = K^-1 rhs with the factor in Lt; fwd_done: rhs already holds Lam^-1 rhs
     __device__ __forceinline__ void solve(const real* rhs, real* dst, const bool fwd_done)
     {
@@ -603,6 +681,7 @@ struct DenseCtx {
         if (row) { st2(dst + 4 * lane, r4[0], r4[1]); st2(dst + 4 * lane + 2, r4[2], r4[3]); }
         __syncwarp();
     }
+#endif
 };
 
 #ifdef QMPC_DENSE_PROF
@@ -858,19 +937,6 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     }
                 }
                 __syncthreads();
-#ifdef QMPC_FACTOR_TWICE                 // experiment: is the first call slower than a repeat (cold code / cold data)?
-                if (trip == T_FIXED) {
-                    for (int e = tid; e < E; e += DN_THREADS) c.tv[e] = c.rt[e];
-                    __syncthreads();
-#if QMPC_DENSE_FACTOR == 1
-                    c.factor_cols(true);
-#else
-                    c.factor(true);
-#endif
-                    for (int e = tid; e < E; e += DN_THREADS) c.rt[e] = c.tv[e];
-                    __syncthreads();
-                }
-#endif
                 DPROF(7);
 #if QMPC_DENSE_FACTOR == 2
                 c.factor_rl1(trip == T_FIXED);
@@ -879,6 +945,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
 #else
                 c.factor(trip == T_FIXED);
 #endif
+                c.scale_for_solves();
             }
             DPROF(2);
             // (3) warp 0: solves, step logic, next trip

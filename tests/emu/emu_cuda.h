@@ -3,6 +3,7 @@
 // with one OS thread per lane (shuffles / __syncwarp = barriers), so that the kernel LOGIC can be checked
 // against the oracle without a GPU.  Never linked into libqmpc.so; the product path has no CPU fallback.
 #pragma once
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
