@@ -210,9 +210,10 @@ void factor_cols_fn(const int oHt, const int oLt, const int oRt, const int oFx, 
 #pragma unroll
                 for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
                 const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;      // i == j for lanes without a tile: a valid address
+                const int qs = rhs ? 0 : 4;             // the right-hand-side lane has one row: it reads it four times (rows 1..3 unused)
                 real li[16];
 #pragma unroll
-                for (int t = 0; t < 16; t += 2) ld2(pi + t, li[t], li[t + 1]);   // (right-hand side lane: rows 1..3 read on into rt; unused)
+                for (int q = 0; q < 4; ++q) { ld2(pi + q * qs, li[q * 4], li[q * 4 + 1]); ld2(pi + q * qs + 2, li[q * 4 + 2], li[q * 4 + 3]); }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -746,7 +747,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
     c.cbar = reinterpret_cast<unsigned long long*>(sm + lay.cbar);
     c.smbase = sm;
     c.fgen = 0;
-    if (tid < N) flag_init(c.cbar + tid);
+    if (tid == 0) for (int k = 0; k < N; ++k) flag_init(c.cbar + k);      // one thread: compute-sanitizer loses mbarrier.init issued by several lanes at once
     const unsigned tile_bytes = (unsigned)(N * WT * sizeof(real));
     // condensing roles: thread t < T accumulates tile t of H; thread DN_THREADS-1-c carries impulse-response column c
     // (c < E) or the free response (c == E) through the stages - the LAST warps, whose tiles join the sum last, so the

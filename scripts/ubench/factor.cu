@@ -17,7 +17,7 @@ template <int V> __global__ void __launch_bounds__(256, 2) k(const double* Hin, 
     double* v = sm + lay.vec;
     c.rt = v + 11 * c.E; c.dR = v + 12 * c.E; c.cl = v + 7 * c.E; c.fx = c.cl;
     c.cbar = reinterpret_cast<unsigned long long*>(sm + lay.cbar); c.fgen = 0; c.smbase = sm;
-    if (tid < N) flag_init(c.cbar + tid);
+    if (tid == 0) for (int kk = 0; kk < N; ++kk) flag_init(c.cbar + kk);
     { int i = 0; while ((i + 1) * (i + 2) / 2 <= tid) ++i; c.ti = i; c.tj = tid - i * (i + 1) / 2; }
     { int cc = 0, start = 0; while (cc < N && start + (N - cc + 1) <= tid) { start += N - cc + 1; ++cc; } c.fj = cc < N ? cc : -1; c.fi = cc + (tid - start); }
     for (int t = tid; t < lay.T * TS; t += 256) c.Ht[t] = Hin[t];
