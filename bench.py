@@ -40,7 +40,7 @@ METRIC = "closed_loop_rti_mpc_rgp_control_steps_per_sec"
 UNIT = "control_steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of the two solver launches of one control step (screening + dense) in the
 # committed ncu --set full capture of the default shape (profiles/r02_solver_summary.txt); a profile constant
-PROFILE_TRAFFIC_BYTES = 342.5e6
+PROFILE_TRAFFIC_BYTES = 345.0e6      # step 60: 268.3 + 55.7 (screening) + 21.0 + 0.0 (dense) MB
 
 
 def parse():
