@@ -19,6 +19,9 @@
 #ifndef QMPC_DENSE_SCALED_SOLVE
 #define QMPC_DENSE_SCALED_SOLVE 1   // triangular sweeps on tiles pre-scaled by their column's diagonal inverse (scale_for_solves); 0: plain sweeps
 #endif
+#ifndef QMPC_DENSE_UNROLL
+#define QMPC_DENSE_UNROLL 2         // unroll factor of the H x and triangular-sweep loops (2: the next step's tile loads overlap the chain)
+#endif
 #ifndef QMPC_DENSE_MATVEC2
 #define QMPC_DENSE_MATVEC2 0        // 1: two threads per row of H x (measured slower under load: -2.7 %, profiles/r02_policy_ab.txt)
 #endif
@@ -26,6 +29,7 @@
 namespace qmpc {
 
 constexpr int DN_THREADS = 256;
+constexpr int DN_UNROLL = QMPC_DENSE_UNROLL;
 constexpr int DN_MAX_N = 21;        // N(N+1)/2 tiles + N right-hand-side threads <= 256
 constexpr int TS = 18;              // reals per 4x4 tile in shared memory: 144 B stride spreads consecutive tiles over the banks
 
@@ -301,6 +305,7 @@ struct DenseCtx {
         if (tid < E) {
             const int I = tid >> 2, ar = tid & 3;
             real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll DN_UNROLL
             for (int J = 0; J <= I; ++J) {
                 const real* p = Ht + tri(I, J) * TS + ar * 4;
                 real h0, h1, h2, h3, x0, x1, x2, x3;
@@ -308,6 +313,7 @@ struct DenseCtx {
                 ld2(x + 4 * J, x0, x1); ld2(x + 4 * J + 2, x2, x3);
                 s0 = fma(h0, x0, s0); s1 = fma(h1, x1, s1); s2 = fma(h2, x2, s2); s3 = fma(h3, x3, s3);
             }
+#pragma unroll DN_UNROLL
             for (int J = I + 1; J < N; ++J) {
                 const real* p = Ht + tri(J, I) * TS + ar;
                 real x0, x1, x2, x3;
@@ -585,6 +591,7 @@ struct DenseCtx {
         Inv4<real> Nme;
         Nme.load(Lt + tri(me, me) * TS);
         if (!fwd_done) {
+#pragma unroll DN_UNROLL
             for (int K = 0; K < N - 1; ++K) {
                 const real* p = Lt + tri(me > K ? me : K + 1, K) * TS;       // a valid tile for every lane
                 real l[16], sk[4];
@@ -609,6 +616,7 @@ struct DenseCtx {
 #pragma unroll
             for (int q = 0; q < 4; ++q) r4[q] = x[q];
         }
+#pragma unroll DN_UNROLL
         for (int K = N - 1; K > 0; --K) {
             const real* p = Lt + tri(K, me < K ? me : K - 1) * TS;
             real l[16], xk[4];
