@@ -22,6 +22,9 @@
 #ifndef QMPC_DENSE_UNROLL
 #define QMPC_DENSE_UNROLL 2         // unroll factor of the H x and triangular-sweep loops (2: the next step's tile loads overlap the chain)
 #endif
+#ifndef QMPC_DENSE_GPLANES
+#define QMPC_DENSE_GPLANES 1        // condensing: impulse-response rows stored as two planes (see gcol)
+#endif
 #ifndef QMPC_DENSE_MATVEC2
 #define QMPC_DENSE_MATVEC2 0        // 1: two threads per row of H x (measured slower under load: -2.7 %, profiles/r02_policy_ab.txt)
 #endif
@@ -762,6 +765,17 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
     // propagation of chunk i+1 overlaps the tile accumulation of chunk i
     const int cidx = DN_THREADS - 1 - tid;
     const bool colthr = cidx <= E;
+    // position of input column c = 4 blk + e inside a row of the impulse-response block.  QMPC_DENSE_GPLANES: two planes, entries
+    // e = 0, 1 of every block contiguous in the first and e = 2, 3 in the second, so the 16-byte loads of a warp whose lanes
+    // walk over the blocks fall into half as many 128-byte wavefronts as with the blocks' four entries side by side
+    auto gcol = [GS](int c) -> int {
+#if QMPC_DENSE_GPLANES
+        return ((c >> 2) << 1) + (c & 1) + ((c >> 1) & 1) * (GS / 2);
+#else
+        (void)GS;
+        return c;
+#endif
+    };
     const int nch = (N + DN_CH - 1) / DN_CH;
     enum { T_FIXED, T_ADJ, T_PRED, T_GRAD, T_DONE };
     __syncthreads();
@@ -840,7 +854,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                 }
                 if (cidx < E) {
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) Gb[(kk * 13 + r) * GS + cidx] = sqk[r] * g[r];
+                    for (int r = 0; r < NX; ++r) Gb[(kk * 13 + r) * GS + gcol(cidx)] = sqk[r] * g[r];
                 } else {
 #pragma unroll
                     for (int r = 0; r < NX; ++r) eb[kk * 16 + r] = sqk[r] * (g[r] + dxs[(k + 1) * NX + r]);
@@ -864,8 +878,13 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
 #pragma unroll
                     for (int r = 0; r < NX; ++r) {
                         real gi[4], gj[4];
+#if QMPC_DENSE_GPLANES
+                        ld2(Gk + r * GS + 2 * ti, gi[0], gi[1]); ld2(Gk + r * GS + GS / 2 + 2 * ti, gi[2], gi[3]);
+                        ld2(Gk + r * GS + 2 * tj, gj[0], gj[1]); ld2(Gk + r * GS + GS / 2 + 2 * tj, gj[2], gj[3]);
+#else
                         ld2(Gk + r * GS + 4 * ti, gi[0], gi[1]); ld2(Gk + r * GS + 4 * ti + 2, gi[2], gi[3]);
                         ld2(Gk + r * GS + 4 * tj, gj[0], gj[1]); ld2(Gk + r * GS + 4 * tj + 2, gj[2], gj[3]);
+#endif
 #pragma unroll
                         for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -879,7 +898,7 @@ __global__ void __launch_bounds__(DN_THREADS, QMPC_DENSE_MIN_CTAS) qmpc_dense_ke
                     if (k >= N) break;
                     if ((tid >> 2) > k) continue;
 #pragma unroll
-                    for (int r = 0; r < NX; ++r) fc = fma(Gb[(kk * 13 + r) * GS + tid], eb[kk * 16 + r], fc);
+                    for (int r = 0; r < NX; ++r) fc = fma(Gb[(kk * 13 + r) * GS + gcol(tid)], eb[kk * 16 + r], fc);
                 }
             }
             __syncthreads();                    // buffer (ch+1)&1 is complete; nobody reads buffer ch&1 any more

@@ -12,7 +12,7 @@ _LIBS = {}
 # build flavours of the emulated kernels: name -> (extra compiler defines, tile row stride)
 FLAVOURS = {"": ([], 18), "noring": (["-DQMPC_RING=0", "-DQMPC_WR=16"], 16), "trace": (["-DQMPC_EMU_TRACE"], 18),
             # the dense kernel's other Cholesky variants (QMPC_DENSE_FACTOR in mpc_kernels_dense.cuh)
-            "factor0": (["-DQMPC_DENSE_FACTOR=0", "-DQMPC_DENSE_SCALED_SOLVE=0"], 18), "factor1": (["-DQMPC_DENSE_FACTOR=1"], 18), "factor2": (["-DQMPC_DENSE_FACTOR=2"], 18)}
+            "factor0": (["-DQMPC_DENSE_FACTOR=0", "-DQMPC_DENSE_SCALED_SOLVE=0", "-DQMPC_DENSE_GPLANES=0"], 18), "factor1": (["-DQMPC_DENSE_FACTOR=1"], 18), "factor2": (["-DQMPC_DENSE_FACTOR=2"], 18)}
 
 
 def lib(flavour=""):
