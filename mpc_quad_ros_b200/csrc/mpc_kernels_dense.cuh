@@ -110,6 +110,7 @@ struct Inv4 {
     }
 };
 
+// The column-per-warp factorisation of DenseCtx::factor_cols (described there), as a free function that is NOT inlined.
 template <typename real>
 #ifdef QMPC_FCOLS_INLINE
 __device__ __forceinline__
@@ -117,150 +118,150 @@ __device__ __forceinline__
 __device__ __noinline__
 #endif
 void factor_cols_fn(const int oHt, const int oLt, const int oRt, const int oFx, const int oDR, const int oCbar,
-                                            const unsigned fgen, const int N, const int tid, const bool fixed)
+                    const unsigned fgen, const int N, const int tid, const bool fixed)
 {
-        // the arrays arrive as offsets into the CTA's dynamic shared memory and are rebuilt from the shared symbol here:
-        // pointer arguments of a non-inlined function are generic, and every access would be a generic LD / ST
-        QMPC_DYN_SMEM(smem_raw);
-        real* const sm = reinterpret_cast<real*>(smem_raw);
-        const real* const Ht = sm + oHt;
-        real* const Lt = sm + oLt;
-        real* const rt = sm + oRt;
-        const real* const fx = sm + oFx;
-        const real* const dR = sm + oDR;
-        unsigned long long* const cbar = reinterpret_cast<unsigned long long*>(sm + oCbar);
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int j = warp; j < N; j += DN_THREADS / 32) {
-            const int rows = N - j;
-            const bool tile = lane > 0 && lane < rows, rhs = lane == rows;
-            const int i = tile ? j + lane : j;
-            // dg: the diagonal tile (j, j), carried REDUNDANTLY by every lane (lower triangle); acc: this lane's own tile
-            real acc[16], dg[16];
-            real kj[4] = {1, 1, 1, 1};
-            {
-                const real* p = Ht + tri(j, j) * TS;
+    // the arrays arrive as offsets into the CTA's dynamic shared memory and are rebuilt from the shared symbol here:
+    // pointer arguments of a non-inlined function are generic, and every access would be a generic LD / ST
+    QMPC_DYN_SMEM(smem_raw);
+    real* const sm = reinterpret_cast<real*>(smem_raw);
+    const real* const Ht = sm + oHt;
+    real* const Lt = sm + oLt;
+    real* const rt = sm + oRt;
+    const real* const fx = sm + oFx;
+    const real* const dR = sm + oDR;
+    unsigned long long* const cbar = reinterpret_cast<unsigned long long*>(sm + oCbar);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < N; j += DN_THREADS / 32) {
+        const int rows = N - j;
+        const bool tile = lane > 0 && lane < rows, rhs = lane == rows;
+        const int i = tile ? j + lane : j;
+        // dg: the diagonal tile (j, j), carried REDUNDANTLY by every lane (lower triangle); acc: this lane's own tile
+        real acc[16], dg[16];
+        real kj[4] = {1, 1, 1, 1};
+        {
+            const real* p = Ht + tri(j, j) * TS;
 #pragma unroll
-                for (int t = 0; t < 16; t += 2) ld2(p + t, dg[t], dg[t + 1]);
-                if (fixed) {
+            for (int t = 0; t < 16; t += 2) ld2(p + t, dg[t], dg[t + 1]);
+            if (fixed) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) kj[q] = fx[4 * j + q] != real(0) ? real(0) : real(1);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) dg[q * 4 + r] *= kj[q] * kj[r];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (kj[q] == real(0)) dg[q * 5] = real(1);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) dg[q * 5] += dR[4 * j + q];
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 16; ++t) acc[t] = 0;
-            if (tile) {
-                const real* p = Ht + tri(i, j) * TS;
-#pragma unroll
-                for (int t = 0; t < 16; t += 2) ld2(p + t, acc[t], acc[t + 1]);
-                if (fixed) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const real ki = fx[4 * i + q] != real(0) ? real(0) : real(1);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[q * 4 + r] *= ki * kj[r];
-                    }
-                }
-            } else if (rhs) {
-                ld2(rt + 4 * j, acc[0], acc[1]); ld2(rt + 4 * j + 2, acc[2], acc[3]);
-            }
-            for (int k = 0; k < j - 1; ++k) {       // look-ahead: columns finished long ago
-                flag_wait(cbar + k, fgen);
-                real lj[16];
-                const real* pj = Lt + tri(j, k) * TS;
-#pragma unroll
-                for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
+                for (int q = 0; q < 4; ++q) kj[q] = fx[4 * j + q] != real(0) ? real(0) : real(1);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int r = 0; r <= q; ++r) {
-                        real s = dg[q * 4 + r];
+                    for (int r = 0; r < 4; ++r) dg[q * 4 + r] *= kj[q] * kj[r];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
-                        dg[q * 4 + r] = s;
-                    }
-                // row q of this lane's left factor: tile (i, k), or the forward-substituted right-hand side of block k
-                const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;
-                const int nq = rhs ? 1 : (tile ? 4 : 0);
+                for (int q = 0; q < 4; ++q) if (kj[q] == real(0)) dg[q * 5] = real(1);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dg[q * 5] += dR[4 * j + q];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = 0;
+        if (tile) {
+            const real* p = Ht + tri(i, j) * TS;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) ld2(p + t, acc[t], acc[t + 1]);
+            if (fixed) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (q < nq) {
-                        real l0, l1, l2, l3;
-                        ld2(pi + q * 4, l0, l1); ld2(pi + q * 4 + 2, l2, l3);
+                    const real ki = fx[4 * i + q] != real(0) ? real(0) : real(1);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            real s = acc[q * 4 + r];
-                            s = fma(-l0, lj[r * 4], s); s = fma(-l1, lj[r * 4 + 1], s);
-                            s = fma(-l2, lj[r * 4 + 2], s); s = fma(-l3, lj[r * 4 + 3], s);
-                            acc[q * 4 + r] = s;
-                        }
-                    }
+                    for (int r = 0; r < 4; ++r) acc[q * 4 + r] *= ki * kj[r];
                 }
             }
-            // The column that has just finished (k = j - 1) is the serial chain of the whole factorisation: its product, the
-            // 4x4 Cholesky of the diagonal tile and the substitution of this lane's rows form ONE basic block (no branch:
-            // idle lanes compute on valid dummy addresses, the reciprocal square roots are branch-free), so the scheduler
-            // moves the 64 FMAs of the lane's own tile into the latency of the Cholesky's dependent chain.
-            if (j > 0) {
-                const int k = j - 1;
-                flag_wait(cbar + k, fgen);
-                real lj[16];
-                const real* pj = Lt + tri(j, k) * TS;
+        } else if (rhs) {
+            ld2(rt + 4 * j, acc[0], acc[1]); ld2(rt + 4 * j + 2, acc[2], acc[3]);
+        }
+        for (int k = 0; k < j - 1; ++k) {       // look-ahead: columns finished long ago
+            flag_wait(cbar + k, fgen);
+            real lj[16];
+            const real* pj = Lt + tri(j, k) * TS;
 #pragma unroll
-                for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
-                const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;      // i == j for lanes without a tile: a valid address
-                const int qs = rhs ? 0 : 4;             // the right-hand-side lane has one row: it reads it four times (rows 1..3 unused)
-                real li[16];
+            for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { ld2(pi + q * qs, li[q * 4], li[q * 4 + 1]); ld2(pi + q * qs + 2, li[q * 4 + 2], li[q * 4 + 3]); }
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int r = 0; r <= q; ++r) {
+                    real s = dg[q * 4 + r];
 #pragma unroll
-                    for (int r = 0; r <= q; ++r) {
-                        real s = dg[q * 4 + r];
+                    for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
+                    dg[q * 4 + r] = s;
+                }
+            // row q of this lane's left factor: tile (i, k), or the forward-substituted right-hand side of block k
+            const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;
+            const int nq = rhs ? 1 : (tile ? 4 : 0);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
-                        dg[q * 4 + r] = s;
-                    }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4; ++q) {
+                if (q < nq) {
+                    real l0, l1, l2, l3;
+                    ld2(pi + q * 4, l0, l1); ld2(pi + q * 4 + 2, l2, l3);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         real s = acc[q * 4 + r];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) s = fma(-li[q * 4 + c], lj[r * 4 + c], s);
+                        s = fma(-l0, lj[r * 4], s); s = fma(-l1, lj[r * 4 + 1], s);
+                        s = fma(-l2, lj[r * 4 + 2], s); s = fma(-l3, lj[r * 4 + 3], s);
                         acc[q * 4 + r] = s;
                     }
-            }
-            // every lane factors the diagonal tile itself: no broadcast, no warp barrier
-            Chol4<real> L;
-            L.template factor<real, true>(dg);
-            real z[16];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) L.fsolve(acc + q * 4, z + q * 4);
-            if (tile) {
-                real* o = Lt + tri(i, j) * TS;
-#pragma unroll
-                for (int t = 0; t < 16; t += 2) st2(o + t, z[t], z[t + 1]);
-            } else if (rhs) {
-                st2(rt + 4 * j, z[0], z[1]); st2(rt + 4 * j + 2, z[2], z[3]);
-            }
-            flag_arrive(cbar + j);
-            if (lane == 0) {            // the inverse of the diagonal factor is only read by solve(), after the closing barrier
-                Inv4<real> Ni;
-                Ni.from(L);
-                Ni.store(Lt + tri(j, j) * TS);
+                }
             }
         }
-        __syncthreads();
+        // The column that has just finished (k = j - 1) is the serial chain of the whole factorisation: its product, the
+        // 4x4 Cholesky of the diagonal tile and the substitution of this lane's rows form ONE basic block (no branch:
+        // idle lanes compute on valid dummy addresses, the reciprocal square roots are branch-free), so the scheduler
+        // moves the 64 FMAs of the lane's own tile into the latency of the Cholesky's dependent chain.
+        if (j > 0) {
+            const int k = j - 1;
+            flag_wait(cbar + k, fgen);
+            real lj[16];
+            const real* pj = Lt + tri(j, k) * TS;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) ld2(pj + t, lj[t], lj[t + 1]);
+            const real* pi = rhs ? rt + 4 * k : Lt + tri(i, k) * TS;      // i == j for lanes without a tile: a valid address
+            const int qs = rhs ? 0 : 4;             // the right-hand-side lane has one row: it reads it four times (rows 1..3 unused)
+            real li[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { ld2(pi + q * qs, li[q * 4], li[q * 4 + 1]); ld2(pi + q * qs + 2, li[q * 4 + 2], li[q * 4 + 3]); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r <= q; ++r) {
+                    real s = dg[q * 4 + r];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s = fma(-lj[q * 4 + c], lj[r * 4 + c], s);
+                    dg[q * 4 + r] = s;
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    real s = acc[q * 4 + r];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s = fma(-li[q * 4 + c], lj[r * 4 + c], s);
+                    acc[q * 4 + r] = s;
+                }
+        }
+        // every lane factors the diagonal tile itself: no broadcast, no warp barrier
+        Chol4<real> L;
+        L.template factor<real, true>(dg);
+        real z[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) L.fsolve(acc + q * 4, z + q * 4);
+        if (tile) {
+            real* o = Lt + tri(i, j) * TS;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) st2(o + t, z[t], z[t + 1]);
+        } else if (rhs) {
+            st2(rt + 4 * j, z[0], z[1]); st2(rt + 4 * j + 2, z[2], z[3]);
+        }
+        flag_arrive(cbar + j);
+        if (lane == 0) {            // the inverse of the diagonal factor is only read by solve(), after the closing barrier
+            Inv4<real> Ni;
+            Ni.from(L);
+            Ni.store(Lt + tri(j, j) * TS);
+        }
+    }
+    __syncthreads();
 }
 
 
